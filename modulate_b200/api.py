@@ -1,0 +1,172 @@
+"""Host-side mirror of the reference's interface for the hot path, over the C ABI."""
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Optional, Tuple
+
+import numpy as np
+
+from . import _abi
+from ._abi import ModError
+
+# numpy view of ``mod_desc``
+DESC_DTYPE = np.dtype([("src_off", "<u8"), ("dst_off", "<u8"), ("len", "<u4"), ("key", "<i4")])
+assert DESC_DTYPE.itemsize == 24
+
+
+def _i32(key: int) -> int:
+    """Reinterpret any 32-bit pattern as the ``int`` the reference's Cycle takes (CArk.cpp:339
+    passes the ``unsigned int`` platform key to an ``int`` parameter)."""
+    key = int(key) & 0xFFFFFFFF
+    return key - (1 << 32) if key & 0x80000000 else key
+
+
+def _buffer_info(buf: Any) -> Tuple[int, int, bool]:
+    """-> (address, nbytes, is_cuda) for bytearray / memoryview / numpy / torch / raw int address."""
+    if isinstance(buf, int):
+        return buf, -1, False
+    if hasattr(buf, "data_ptr") and hasattr(buf, "is_cuda"):  # torch.Tensor, without importing torch
+        if not buf.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return buf.data_ptr(), buf.numel() * buf.element_size(), bool(buf.is_cuda)
+    if isinstance(buf, np.ndarray):
+        if not buf.flags["C_CONTIGUOUS"]:
+            raise ValueError("array must be C-contiguous")
+        if not buf.flags["WRITEABLE"]:
+            raise ValueError("array must be writeable (Cycle works in place)")
+        return buf.ctypes.data, buf.nbytes, False
+    if isinstance(buf, (bytearray, memoryview)):
+        mv = memoryview(buf)
+        if mv.readonly:
+            raise ValueError("buffer must be writeable (Cycle works in place)")
+        c = (ctypes.c_char * mv.nbytes).from_buffer(mv)
+        return ctypes.addressof(c), mv.nbytes, False
+    raise TypeError(f"unsupported buffer type {type(buf)!r}")
+
+
+def init(device: int = -1) -> None:
+    _abi.check(_abi.load().mod_init(device))
+
+
+def device_count() -> int:
+    return _abi.check(_abi.load().mod_device_count())
+
+
+def launch_count() -> int:
+    return int(_abi.load().mod_launch_count())
+
+
+def key_jump(key: int, pos: int) -> int:
+    """Key whose stream equals `key`'s stream from byte `pos` on (O(log pos) jump-ahead)."""
+    return int(_abi.load().mod_key_jump(_i32(key), int(pos)))
+
+
+def cycle(buf: Any, size: Optional[int], key: int) -> None:
+    """``CEncryptionCycler::Cycle`` in place on a host or device buffer (synchronous)."""
+    addr, nbytes, _ = _buffer_info(buf)
+    if size is None:
+        size = nbytes
+    if nbytes >= 0 and size > nbytes:
+        raise ValueError(f"liDataSize {size} exceeds the {nbytes}-byte buffer")
+    _abi.check(_abi.load().mod_cycle(addr, int(size), _i32(key)))
+
+
+def cycle_device(src: Any, dst: Any, size: int, key: int, stream: int = 0) -> None:
+    """Asynchronous device-resident Cycle (src may equal dst)."""
+    s_addr, s_n, _ = _buffer_info(src)
+    d_addr, d_n, _ = _buffer_info(dst)
+    if (s_n >= 0 and size > s_n) or (d_n >= 0 and size > d_n):
+        raise ValueError("size exceeds a buffer")
+    _abi.check(_abi.load().mod_cycle_device(s_addr, d_addr, int(size), _i32(key), stream or None))
+
+
+class CEncryptionCycler:
+    """Same surface as the reference class (``CEncryptionCycler.h:3-10``): stateless, one method."""
+
+    def Cycle(self, lpData: Any, liDataSize: Optional[int], liInitialKey: int) -> None:
+        cycle(lpData, liDataSize, liInitialKey)
+
+
+def make_descs(src_off, dst_off, length, key) -> np.ndarray:
+    n = len(src_off)
+    d = np.zeros(n, dtype=DESC_DTYPE)
+    d["src_off"] = src_off
+    d["dst_off"] = dst_off
+    d["len"] = length
+    d["key"] = np.asarray(key, dtype=np.int64).astype(np.uint32).view(np.int32) \
+        if not isinstance(key, np.ndarray) or key.dtype != np.int32 else key
+    return d
+
+
+def _descs(descs: np.ndarray) -> np.ndarray:
+    d = np.ascontiguousarray(descs, dtype=DESC_DTYPE)
+    return d
+
+
+class Plan:
+    """Descriptors + tile map resident in HBM; ``run`` is one launch of the batched kernel."""
+
+    def __init__(self, descs: np.ndarray, src_bytes: int, dst_bytes: int, dst_align: int = 0):
+        d = _descs(descs)
+        self._handle = ctypes.c_void_p()
+        self._lib = _abi.load()
+        _abi.check(self._lib.mod_plan_create(d.ctypes.data if len(d) else None, len(d), int(src_bytes),
+                                             int(dst_bytes), int(dst_align), ctypes.byref(self._handle)))
+        self.n = len(d)
+
+    @property
+    def payload_bytes(self) -> int:
+        return int(self._lib.mod_plan_payload_bytes(self._handle))
+
+    @property
+    def num_tiles(self) -> int:
+        return int(self._lib.mod_plan_num_tiles(self._handle))
+
+    def run(self, src: Any, dst: Any, stream: int = 0) -> None:
+        s_addr, _, _ = _buffer_info(src)
+        d_addr, _, _ = _buffer_info(dst)
+        _abi.check(self._lib.mod_plan_run(self._handle, s_addr, d_addr, stream or None))
+
+    def close(self) -> None:
+        if self._handle:
+            self._lib.mod_plan_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def cycle_batch(descs: np.ndarray, src: Any, dst: Any, src_bytes: Optional[int] = None,
+                dst_bytes: Optional[int] = None) -> None:
+    """Gather/scatter + per-entry Cycle for every descriptor (synchronous; host or device buffers)."""
+    d = _descs(descs)
+    s_addr, s_n, _ = _buffer_info(src)
+    d_addr, d_n, _ = _buffer_info(dst)
+    src_bytes = s_n if src_bytes is None else src_bytes
+    dst_bytes = d_n if dst_bytes is None else dst_bytes
+    if src_bytes < 0 or dst_bytes < 0:
+        raise ValueError("buffer sizes are required with raw addresses")
+    _abi.check(_abi.load().mod_cycle_batch(d.ctypes.data if len(d) else None, len(d), s_addr, int(src_bytes),
+                                           d_addr, int(dst_bytes)))
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    b, e = ctypes.c_uint64(), ctypes.c_uint64()
+    _abi.check(_abi.load().mod_shard_range(int(total), rank, world, ctypes.byref(b), ctypes.byref(e)))
+    return int(b.value), int(e.value)
+
+
+def shard_descs(descs: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Rank's share of a descriptor list, balanced by payload bytes (large entries are cut and
+    the tail piece gets the jumped key)."""
+    d = _descs(descs)
+    L = _abi.load()
+    ptr = d.ctypes.data if len(d) else None
+    n = _abi.check(L.mod_shard_descs(ptr, len(d), rank, world, None, 0))
+    out = np.zeros(n, dtype=DESC_DTYPE)
+    if n:
+        _abi.check(L.mod_shard_descs(ptr, len(d), rank, world, out.ctypes.data, n))
+    return out

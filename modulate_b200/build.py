@@ -1,0 +1,73 @@
+"""Build the sm_100a shared library (kernels + C ABI + C++ facade) in-tree with nvcc.
+
+    python -m modulate_b200.build [--force]
+
+The result, ``modulate_b200/libmodulate_b200.so``, is git-ignored but travels to the GPU box
+with the gpurun snapshot.  There is no JIT and no fallback: if the library cannot be built or
+loaded, importing the compute API raises.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libmodulate_b200.so")
+CLI = os.path.join(PKG, "bin", "modulate")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-Wall,-Wno-unknown-pragmas",
+    "-cudart", "static",
+]
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
+
+
+def _sources() -> list[str]:
+    return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
+
+
+def _deps() -> list[str]:
+    return _sources() + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + \
+        glob.glob(os.path.join(ROOT, "include", "*.h")) + glob.glob(os.path.join(CSRC, "cli", "*.cpp"))
+
+
+def stale(target: str) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if force or stale(LIB):
+        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+               "-o", LIB, *_sources()]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    cli_src = sorted(glob.glob(os.path.join(CSRC, "cli", "*.cpp")))
+    if cli_src and (force or stale(CLI)):
+        os.makedirs(os.path.dirname(CLI), exist_ok=True)
+        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+               "-o", CLI, *cli_src, "-L", PKG, "-lmodulate_b200", "-Wl,-rpath,$ORIGIN/..", "-ldl", "-lpthread"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,358 @@
+// cycle_kernels.cu -- hand-written sm_100a kernels for the Modulate keystream path.
+//
+// What the kernel computes (per descriptor {src_off, dst_off, len, key}):
+//     dst[dst_off + i] = src[src_off + i] ^ low8(k0 * a^(i+1) mod m) ^ 0xFF,   0 <= i < len
+// which is CEncryptionCycler::Cycle (reference CEncryptionCycler.cpp:4-14) applied to a copy of
+// the entry -- the copy being CArk::ExtractFiles' gather (CArk.cpp:494) or CArk::BuildArk's
+// scatter (CArk.cpp:807-811).  One variable-length batched kernel serves every caller; a
+// contiguous Cycle() is the same kernel with a few descriptors passed in the parameter block.
+//
+// Decomposition (B200: HBM-bound byte work, co-limited by the integer pipes -- no tensor cores):
+//   * destination space is cut into 16-byte aligned chunks; one thread owns one chunk per round
+//     and moves it with one 128-bit load and one 128-bit store, a warp covering 512 contiguous
+//     bytes per round (fully coalesced), kIters rounds per tile;
+//   * the serial recurrence is broken by modular jump-ahead: per tile a handful of table
+//     multiplies (a^(tile), a^(16*lane), a^(-head)) give each thread the state just before its
+//     chunk; rounds advance by the constant a^512; inside the chunk the state is stepped 16
+//     times with a lazily reduced Mersenne fold (IMAD.WIDE + one add) -- about 4 integer
+//     instructions per payload byte in total;
+//   * entries are byte-packed (BuildArk leaves no padding), so source and destination are
+//     generally misaligned with respect to each other: the source is read as aligned 16-byte
+//     granules, the neighbouring granule comes from the next lane by warp shuffle, and a
+//     funnel shift re-aligns them; only the first and last chunk of an entry take a byte path.
+#include "cycle_kernels.cuh"
+#include "lcg.h"
+
+namespace modk {
+
+using modlcg::mulmod;
+using modlcg::step_lazy;
+using modlcg::low8_canonical;
+
+constexpr int kUnroll = 4;  // independent 16-byte chunks in flight per thread
+static_assert(kIters % kUnroll == 0, "rounds per tile must be a multiple of the unroll");
+
+// tile index within an entry < 2^32 / kTileBytes + 1; split 10 bits low / rest high
+constexpr int kTw0Size = 1024;
+constexpr int kTw1Size = (int)(((1ull << 32) / kTileBytes) / kTw0Size + 2);
+
+__constant__ uint32_t c_tw0[kTw0Size];  // a^(kTileBytes * j)
+__constant__ uint32_t c_tw1[kTw1Size];  // a^(kTileBytes * 1024 * j)
+__constant__ uint32_t c_ainv[16];       // a^(-h): rewinds the stream to the chunk grid origin
+__device__ uint32_t g_chunk_pow[kChunksPerTile];  // a^(16 * j): lane-divergent index, so HBM/L1 rather than the constant bank
+
+constexpr uint32_t kRoundJump = modlcg::pow_a(512);  // one round = 32 lanes x 16 bytes further down the stream
+
+// ---- 128-bit global accesses (explicit state space: the addresses are rebuilt from integers) ------
+
+__device__ __forceinline__ uint4 ldg128(uint64_t addr)
+{
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(addr));
+    return r;
+}
+
+__device__ __forceinline__ void stg128(uint64_t addr, const uint4& v)
+{
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+// ---- per-chunk arithmetic -------------------------------------------------------------------
+
+// XOR the 16 bytes of `d` with the keystream that follows (negated) state `s`, the state just
+// before the chunk's first byte.  Per byte: IMAD.WIDE + LEA.HI (step), LEA.HI (canonical low
+// byte); per word: three PRMTs pack four keystream bytes and one LOP3 applies them.
+__device__ __forceinline__ uint4 cycle_chunk(uint4 d, uint32_t s)
+{
+    uint32_t w[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s = step_lazy(s);
+        const uint32_t b0 = low8_canonical(s);
+        s = step_lazy(s);
+        const uint32_t b1 = low8_canonical(s);
+        s = step_lazy(s);
+        const uint32_t b2 = low8_canonical(s);
+        s = step_lazy(s);
+        const uint32_t b3 = low8_canonical(s);
+        const uint32_t lo = __byte_perm(b0, b1, 0x0040);
+        const uint32_t hi = __byte_perm(b2, b3, 0x0040);
+        w[j] ^= __byte_perm(lo, hi, 0x5410);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---- one tile = one warp ------------------------------------------------------------------------
+
+struct TileGeom {
+    uint64_t dst_al;    // 16-byte aligned address of chunk 0
+    uint64_t src_al;    // 16-byte aligned address of the granule holding chunk 0's first source byte
+    uint64_t dst_addr;  // address of the entry's first destination byte
+    uint64_t src_addr;  // address of the entry's first source byte
+    uint32_t len;
+    uint32_t h0;        // dst_addr & 15
+    uint32_t shift;     // byte offset of chunk data inside its first source granule (0 = co-aligned)
+    uint32_t c_begin, c_end;  // chunk range of this tile
+    uint32_t f_lo, f_hi;      // chunks in [f_lo, f_hi) are interior: whole-granule loads, 128-bit store
+};
+
+// Edge chunk (first / last chunk of an entry, or one whose source granules would leave the
+// source buffer): byte-granular and predicated.  Out of line -- at most a couple per entry.
+__device__ __noinline__ void edge_chunk(const uint8_t* src_entry, uint8_t* dst_entry, long long pos0,
+                                        uint32_t len, uint32_t s)
+{
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        const long long pos = pos0 + b;
+        if (pos >= 0 && pos < (long long)len)
+            w[b >> 2] |= (uint32_t)src_entry[pos] << (8 * (b & 3));
+    }
+    const uint4 o = cycle_chunk(make_uint4(w[0], w[1], w[2], w[3]), s);
+    const uint32_t r[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+        const long long pos = pos0 + b;
+        if (pos >= 0 && pos < (long long)len)
+            dst_entry[pos] = (uint8_t)(r[b >> 2] >> (8 * (b & 3)));
+    }
+}
+
+// Interior chunks of the tile: kUnroll independent 128-bit loads in flight per thread.
+template <bool kCoAligned>
+__device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, const uint32_t lane)
+{
+    const uint32_t ws = g.shift >> 2;
+    const uint32_t bs = (g.shift & 3u) * 8u;
+    const uint32_t m_hi = min(g.c_end, g.f_hi);
+
+#pragma unroll 1
+    for (uint32_t base = g.c_begin; base < m_hi; base += 32u * kUnroll) {
+        uint4 own[kUnroll];
+        uint4 nbr[kUnroll];
+        bool fast[kUnroll];
+
+        // phase 1: every load of the unrolled group is issued before anything consumes one
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t c = base + (uint32_t)u * 32u + lane;
+            fast[u] = (c >= g.f_lo) && (c < m_hi);
+            own[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (fast[u])
+                own[u] = ldg128(g.src_al + 16ull * c);
+            if (!kCoAligned) {
+                nbr[u] = make_uint4(0u, 0u, 0u, 0u);
+                // the next granule normally arrives by shuffle from lane+1; lane 31 and the last
+                // interior lane have no such neighbour and fetch it themselves
+                if (fast[u] && (lane == 31u || c + 1u >= m_hi))
+                    nbr[u] = ldg128(g.src_al + 16ull * c + 16ull);
+            }
+        }
+
+        // phase 2: re-align, cipher, store
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t c = base + (uint32_t)u * 32u + lane;
+            uint4 data = own[u];
+            if (!kCoAligned) {
+                uint4 nx;
+                nx.x = __shfl_down_sync(0xFFFFFFFFu, own[u].x, 1);
+                nx.y = __shfl_down_sync(0xFFFFFFFFu, own[u].y, 1);
+                nx.z = __shfl_down_sync(0xFFFFFFFFu, own[u].z, 1);
+                nx.w = __shfl_down_sync(0xFFFFFFFFu, own[u].w, 1);
+                if (lane == 31u || c + 1u >= m_hi)
+                    nx = nbr[u];
+                uint32_t w0 = own[u].x, w1 = own[u].y, w2 = own[u].z, w3 = own[u].w;
+                uint32_t w4 = nx.x, w5 = nx.y, w6 = nx.z, w7 = nx.w;
+                if (ws & 2u) {
+                    w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = w7;
+                }
+                if (ws & 1u) {
+                    w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5;
+                }
+                data.x = __funnelshift_r(w0, w1, bs);
+                data.y = __funnelshift_r(w1, w2, bs);
+                data.z = __funnelshift_r(w2, w3, bs);
+                data.w = __funnelshift_r(w3, w4, bs);
+            }
+            if (fast[u])
+                stg128(g.dst_al + 16ull * c, cycle_chunk(data, v));
+            v = mulmod(v, kRoundJump);  // state just before this lane's chunk of the next round
+        }
+    }
+}
+
+__device__ __forceinline__ void run_tile(const BatchArgs& a, const DevDesc& d, const uint32_t tile,
+                                         const uint32_t lane)
+{
+    TileGeom g;
+    const uint32_t tin = tile - d.first_tile;  // tile index inside the entry
+    g.len = d.len;
+    g.dst_addr = (uint64_t)a.dst + d.dst_off;
+    g.src_addr = (uint64_t)a.src + d.src_off;
+    g.h0 = (uint32_t)g.dst_addr & 15u;
+    g.dst_al = g.dst_addr - g.h0;
+    const uint64_t sv = g.src_addr - g.h0;  // source address that pairs with chunk 0, byte 0
+    g.shift = (uint32_t)sv & 15u;
+    g.src_al = sv - g.shift;
+
+    const uint64_t span = (uint64_t)g.h0 + d.len;  // bytes from the chunk grid origin to the entry end
+    const uint32_t nchunks = (uint32_t)((span + 15u) >> 4);
+    g.c_begin = tin * (uint32_t)kChunksPerTile;
+    g.c_end = min(g.c_begin + (uint32_t)kChunksPerTile, nchunks);
+
+    // interior chunks: all 16 destination bytes belong to the entry, and the one or two source
+    // granules they need lie wholly inside the source buffer
+    long long f_lo = g.h0 ? 1 : 0;
+    long long f_hi = (long long)(span >> 4);
+    const long long g_lo = ((long long)(a.src_lo16 - g.src_al)) >> 4;
+    const long long g_hi = (((long long)(a.src_hi16 - g.src_al)) >> 4) - (g.shift ? 1 : 0);
+    f_lo = max(f_lo, g_lo);
+    f_hi = min(f_hi, g_hi);
+    f_hi = max(f_hi, 0ll);
+    f_lo = min(f_lo, f_hi);
+    g.f_lo = (uint32_t)f_lo;
+    g.f_hi = (uint32_t)f_hi;
+
+    // (negated) state just before byte (16*c_begin - h0) of the entry:
+    //   n0 * a^(-h0) * a^(kTileBytes * tin);   chunk c of the tile is a^(16*(c - c_begin)) further on
+    uint32_t st = modlcg::key_to_neg_state(d.key);
+    st = mulmod(st, c_ainv[g.h0]);
+    st = mulmod(st, mulmod(c_tw0[tin & (uint32_t)(kTw0Size - 1)], c_tw1[tin / (uint32_t)kTw0Size]));
+
+    // edge chunks first (rare: skipped for tiles that are interior throughout)
+    if (g.c_begin < g.f_lo || g.c_end > g.f_hi) {
+        for (uint32_t c = g.c_begin + lane; c < g.c_end; c += 32u) {
+            if (c >= g.f_lo && c < g.f_hi)
+                continue;
+            edge_chunk(reinterpret_cast<const uint8_t*>(g.src_addr), reinterpret_cast<uint8_t*>(g.dst_addr),
+                       16ll * (long long)c - (long long)g.h0, g.len,
+                       mulmod(st, g_chunk_pow[c - g.c_begin]));
+        }
+    }
+
+    const uint32_t v = mulmod(st, g_chunk_pow[lane]);
+    if (g.shift == 0u)
+        process_interior<true>(g, v, lane);
+    else
+        process_interior<false>(g, v, lane);
+}
+
+__device__ __forceinline__ DevDesc load_desc(const DevDesc* p)
+{
+    const uint4 lo = reinterpret_cast<const uint4*>(p)[0];
+    const uint4 hi = reinterpret_cast<const uint4*>(p)[1];
+    DevDesc d;
+    d.src_off = (uint64_t)lo.x | ((uint64_t)lo.y << 32);
+    d.dst_off = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
+    d.len = hi.x;
+    d.key = (int32_t)hi.y;
+    d.first_tile = hi.z;
+    d.pad = hi.w;
+    return d;
+}
+
+__global__ void __launch_bounds__(kThreadsPerCta) cycle_batch_kernel(const BatchArgs a)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tile = blockIdx.x * (uint32_t)kWarpsPerCta + (threadIdx.x >> 5);
+    if (tile >= a.n_tiles)
+        return;
+    const uint32_t e = a.tile_entry ? a.tile_entry[tile] : tile / a.tiles_per_entry;
+    const DevDesc d = load_desc(a.descs + e);
+    run_tile(a, d, tile, lane);
+}
+
+// Same kernel with the (few) descriptors in the parameter block: nothing to upload, nothing to
+// allocate, so a contiguous Cycle() is a single asynchronous launch.
+__global__ void __launch_bounds__(kThreadsPerCta)
+cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tile = blockIdx.x * (uint32_t)kWarpsPerCta + (threadIdx.x >> 5);
+    if (tile >= a.n_tiles)
+        return;
+    const uint32_t e = tile / a.tiles_per_entry;
+    const DevDesc d = in.d[e];
+    run_tile(a, d, tile, lane);
+}
+
+// tile -> entry map: the last entry whose first_tile <= tile (entries with no tiles share their
+// successor's first_tile and are skipped by taking the last).
+__global__ void fill_tile_map_kernel(const DevDesc* __restrict__ descs, uint32_t n_descs,
+                                     uint32_t* __restrict__ tile_entry, uint32_t n_tiles)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles)
+        return;
+    uint32_t lo = 0, hi = n_descs;  // invariant: first_tile[lo] <= t, first_tile[hi] > t (hi == n: sentinel)
+    while (hi - lo > 1) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (descs[mid].first_tile <= t)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    tile_entry[t] = lo;
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+
+cudaError_t upload_tables()
+{
+    static uint32_t h_tw0[kTw0Size], h_tw1[kTw1Size], h_ainv[16], h_chunk[kChunksPerTile];
+    static bool built = false;
+    if (!built) {
+        for (int j = 0; j < kTw0Size; ++j)
+            h_tw0[j] = modlcg::pow_a((uint64_t)kTileBytes * (uint64_t)j);
+        for (int j = 0; j < kTw1Size; ++j)
+            h_tw1[j] = modlcg::pow_a((uint64_t)kTileBytes * (uint64_t)kTw0Size * (uint64_t)j);
+        for (int h = 0; h < 16; ++h)
+            h_ainv[h] = modlcg::pow_a_inv((uint64_t)h);
+        for (int j = 0; j < kChunksPerTile; ++j)
+            h_chunk[j] = modlcg::pow_a(16ull * (uint64_t)j);
+        built = true;
+    }
+    cudaError_t err;
+    if ((err = cudaMemcpyToSymbol(c_tw0, h_tw0, sizeof(h_tw0))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_tw1, h_tw1, sizeof(h_tw1))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_ainv, h_ainv, sizeof(h_ainv))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(g_chunk_pow, h_chunk, sizeof(h_chunk))) != cudaSuccess) return err;
+    return cudaSuccess;
+}
+
+static inline unsigned grid_for_tiles(uint32_t n_tiles)
+{
+    return (unsigned)((n_tiles + (uint32_t)kWarpsPerCta - 1u) / (uint32_t)kWarpsPerCta);
+}
+
+cudaError_t launch_batch(const BatchArgs& args, cudaStream_t stream)
+{
+    if (args.n_tiles == 0)
+        return cudaSuccess;
+    cycle_batch_kernel<<<grid_for_tiles(args.n_tiles), kThreadsPerCta, 0, stream>>>(args);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_batch_inline(const BatchArgs& args, const InlineDescs& descs, cudaStream_t stream)
+{
+    if (args.n_tiles == 0)
+        return cudaSuccess;
+    cycle_inline_kernel<<<grid_for_tiles(args.n_tiles), kThreadsPerCta, 0, stream>>>(args, descs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_tile_map(const DevDesc* descs, uint32_t n_descs, uint32_t* tile_entry,
+                                 uint32_t n_tiles, cudaStream_t stream)
+{
+    if (n_tiles == 0)
+        return cudaSuccess;
+    const unsigned threads = 256;
+    fill_tile_map_kernel<<<(n_tiles + threads - 1) / threads, threads, 0, stream>>>(descs, n_descs,
+                                                                                    tile_entry, n_tiles);
+    return cudaGetLastError();
+}
+
+}  // namespace modk

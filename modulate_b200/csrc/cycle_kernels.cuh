@@ -1,0 +1,60 @@
+// cycle_kernels.cuh -- launch interface of the sm_100a keystream kernels (see cycle_kernels.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace modk {
+
+// Geometry of the work decomposition.  A "chunk" is one 16-byte, 16-byte-aligned piece of the
+// DESTINATION address space; a "tile" is what one warp processes: kIters rounds of 32 chunks.
+constexpr int kIters = 8;
+constexpr int kChunksPerTile = 32 * kIters;           // 256 chunks
+constexpr uint32_t kTileBytes = 16u * kChunksPerTile;  // 4 KiB of destination per warp
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreadsPerCta = 32 * kWarpsPerCta;
+constexpr int kMaxInlineDescs = 64;  // descriptors that travel in the kernel parameter block
+
+// Device-side descriptor: mod_desc plus the index of the entry's first tile (32 bytes, two LDG.128).
+struct __align__(16) DevDesc {
+    uint64_t src_off;
+    uint64_t dst_off;
+    uint32_t len;
+    int32_t key;
+    uint32_t first_tile;
+    uint32_t pad;
+};
+
+struct InlineDescs {
+    DevDesc d[kMaxInlineDescs];
+};
+
+struct BatchArgs {
+    const uint8_t* src;
+    uint8_t* dst;
+    const DevDesc* descs;        // HBM descriptors (nullptr in inline mode)
+    const uint32_t* tile_entry;  // tile -> entry map (nullptr: entry = tile / tiles_per_entry)
+    uint32_t n_tiles;
+    uint32_t tiles_per_entry;
+    // 16-byte granules of the source may be loaded whole only inside [src_lo16, src_hi16).
+    uint64_t src_lo16;
+    uint64_t src_hi16;
+};
+
+// Number of tiles an entry of `len` bytes occupies when its first destination byte sits at
+// (address & 15) == h0.
+__host__ __device__ inline uint32_t tiles_for_entry(uint32_t h0, uint32_t len)
+{
+    if (len == 0)
+        return 0;
+    const uint64_t chunks = ((uint64_t)h0 + len + 15u) >> 4;
+    return (uint32_t)((chunks + kChunksPerTile - 1) / kChunksPerTile);
+}
+
+cudaError_t upload_tables();  // jump tables -> __constant__ memory of the current device
+cudaError_t launch_batch(const BatchArgs& args, cudaStream_t stream);
+cudaError_t launch_batch_inline(const BatchArgs& args, const InlineDescs& descs, cudaStream_t stream);
+cudaError_t launch_fill_tile_map(const DevDesc* descs, uint32_t n_descs, uint32_t* tile_entry,
+                                 uint32_t n_tiles, cudaStream_t stream);
+
+}  // namespace modk
