@@ -11,7 +11,8 @@ import os
 
 from . import build as _build
 
-_LIB_PATH = _build.LIB
+# MODULATE_B200_LIB selects an alternative build of the same library (kernel tuning variants)
+_LIB_PATH = os.environ.get("MODULATE_B200_LIB") or _build.LIB
 
 
 class ModDesc(ctypes.Structure):
@@ -68,7 +69,7 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if _build.stale(_LIB_PATH):
+    if _LIB_PATH == _build.LIB and _build.stale(_LIB_PATH):
         try:
             _build.build()
         except Exception as exc:  # no nvcc on this box: a prebuilt .so is still acceptable

@@ -18,8 +18,13 @@
 //     instructions per payload byte in total;
 //   * entries are byte-packed (BuildArk leaves no padding), so source and destination are
 //     generally misaligned with respect to each other: the source is read as aligned 16-byte
-//     granules, the neighbouring granule comes from the next lane by warp shuffle, and a
-//     funnel shift re-aligns them; only the first and last chunk of an entry take a byte path.
+//     granules (each lane takes the two granules its chunk straddles; the second is an L1 hit on
+//     its neighbour's first) and a funnel shift re-aligns them, the word part of the shift being
+//     a template parameter so no register-select network is needed; only the first and last
+//     chunk of an entry take a byte path;
+//   * the grid is persistent (SM count x resident CTAs): each warp strides over tiles and
+//     prefetches the next tile's 32-byte record while it streams the current one, so no warp
+//     ever waits on a chain of dependent metadata loads.
 #include "cycle_kernels.cuh"
 #include "lcg.h"
 
@@ -29,7 +34,18 @@ using modlcg::mulmod;
 using modlcg::step_lazy;
 using modlcg::low8_canonical;
 
-constexpr int kUnroll = 4;  // independent 16-byte chunks in flight per thread
+// ---- tuning knobs (defaults chosen from the measurements in profiles/) ------------------------------
+#ifndef MODK_UNROLL
+#define MODK_UNROLL 4            // independent 16-byte chunks in flight per thread
+#endif
+#ifndef MODK_CANON_FMA_MASK
+#define MODK_CANON_FMA_MASK 0x5  // which of every 4 bytes canonicalise on the FMA pipe (IMAD.HI) vs ALU (LEA.HI)
+#endif
+#ifndef MODK_MIN_CTAS
+#define MODK_MIN_CTAS 3          // resident CTAs per SM requested through __launch_bounds__
+#endif
+
+constexpr int kUnroll = MODK_UNROLL;
 static_assert(kIters % kUnroll == 0, "rounds per tile must be a multiple of the unroll");
 
 // tile index within an entry < 2^32 / kTileBytes + 1; split 10 bits low / rest high
@@ -61,22 +77,34 @@ __device__ __forceinline__ void stg128(uint64_t addr, const uint4& v)
 
 // ---- per-chunk arithmetic -------------------------------------------------------------------
 
+// low8_canonical on the FMA pipe: hi32(s * 2) + s == (s >> 31) + s.  The integer pipes are the
+// co-limiter of this kernel and the ALU pipe carries the fold and the byte packing, so the
+// canonicalisation is issued as an IMAD.HI instead of a second LEA.HI.
+// `two` is the constant 2 delivered through the kernel parameter block: with a literal, ptxas
+// strength-reduces the multiply back into an ALU-pipe LEA.HI.
+__device__ __forceinline__ uint32_t low8_canonical_fma(uint32_t s, uint32_t two)
+{
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, %2, %1;" : "=r"(r) : "r"(s), "r"(two));
+    return r;
+}
+
 // XOR the 16 bytes of `d` with the keystream that follows (negated) state `s`, the state just
-// before the chunk's first byte.  Per byte: IMAD.WIDE + LEA.HI (step), LEA.HI (canonical low
+// before the chunk's first byte.  Per byte: IMAD.WIDE + LEA.HI (step), IMAD.HI (canonical low
 // byte); per word: three PRMTs pack four keystream bytes and one LOP3 applies them.
-__device__ __forceinline__ uint4 cycle_chunk(uint4 d, uint32_t s)
+__device__ __forceinline__ uint4 cycle_chunk(uint4 d, uint32_t s, const uint32_t two)
 {
     uint32_t w[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         s = step_lazy(s);
-        const uint32_t b0 = low8_canonical(s);
+        const uint32_t b0 = (MODK_CANON_FMA_MASK & 1) ? low8_canonical_fma(s, two) : low8_canonical(s);
         s = step_lazy(s);
-        const uint32_t b1 = low8_canonical(s);
+        const uint32_t b1 = (MODK_CANON_FMA_MASK & 2) ? low8_canonical_fma(s, two) : low8_canonical(s);
         s = step_lazy(s);
-        const uint32_t b2 = low8_canonical(s);
+        const uint32_t b2 = (MODK_CANON_FMA_MASK & 4) ? low8_canonical_fma(s, two) : low8_canonical(s);
         s = step_lazy(s);
-        const uint32_t b3 = low8_canonical(s);
+        const uint32_t b3 = (MODK_CANON_FMA_MASK & 8) ? low8_canonical_fma(s, two) : low8_canonical(s);
         const uint32_t lo = __byte_perm(b0, b1, 0x0040);
         const uint32_t hi = __byte_perm(b2, b3, 0x0040);
         w[j] ^= __byte_perm(lo, hi, 0x5410);
@@ -101,7 +129,7 @@ struct TileGeom {
 // Edge chunk (first / last chunk of an entry, or one whose source granules would leave the
 // source buffer): byte-granular and predicated.  Out of line -- at most a couple per entry.
 __device__ __noinline__ void edge_chunk(const uint8_t* src_entry, uint8_t* dst_entry, long long pos0,
-                                        uint32_t len, uint32_t s)
+                                        uint32_t len, uint32_t s, uint32_t two)
 {
     uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -110,7 +138,7 @@ __device__ __noinline__ void edge_chunk(const uint8_t* src_entry, uint8_t* dst_e
         if (pos >= 0 && pos < (long long)len)
             w[b >> 2] |= (uint32_t)src_entry[pos] << (8 * (b & 3));
     }
-    const uint4 o = cycle_chunk(make_uint4(w[0], w[1], w[2], w[3]), s);
+    const uint4 o = cycle_chunk(make_uint4(w[0], w[1], w[2], w[3]), s, two);
     const uint32_t r[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
     for (int b = 0; b < 16; ++b) {
@@ -120,18 +148,20 @@ __device__ __noinline__ void edge_chunk(const uint8_t* src_entry, uint8_t* dst_e
     }
 }
 
-// Interior chunks of the tile: kUnroll independent 128-bit loads in flight per thread.
-template <bool kCoAligned>
-__device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, const uint32_t lane)
+// Interior chunks of the tile: kUnroll independent chunks in flight per thread.
+// kWs < 0: source and destination are co-aligned (one load per chunk).  kWs in 0..3: the chunk
+// starts kWs words (+ a runtime 0..3 bytes) into its first granule and straddles two.
+template <int kWs>
+__device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, const uint32_t lane,
+                                                 const uint32_t two)
 {
-    const uint32_t ws = g.shift >> 2;
     const uint32_t bs = (g.shift & 3u) * 8u;
     const uint32_t m_hi = min(g.c_end, g.f_hi);
 
 #pragma unroll 1
     for (uint32_t base = g.c_begin; base < m_hi; base += 32u * kUnroll) {
         uint4 own[kUnroll];
-        uint4 nbr[kUnroll];
+        uint4 nxt[kUnroll];
         bool fast[kUnroll];
 
         // phase 1: every load of the unrolled group is issued before anything consumes one
@@ -140,14 +170,11 @@ __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, 
             const uint32_t c = base + (uint32_t)u * 32u + lane;
             fast[u] = (c >= g.f_lo) && (c < m_hi);
             own[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (fast[u])
+            nxt[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (fast[u]) {
                 own[u] = ldg128(g.src_al + 16ull * c);
-            if (!kCoAligned) {
-                nbr[u] = make_uint4(0u, 0u, 0u, 0u);
-                // the next granule normally arrives by shuffle from lane+1; lane 31 and the last
-                // interior lane have no such neighbour and fetch it themselves
-                if (fast[u] && (lane == 31u || c + 1u >= m_hi))
-                    nbr[u] = ldg128(g.src_al + 16ull * c + 16ull);
+                if (kWs >= 0)
+                    nxt[u] = ldg128(g.src_al + 16ull * c + 16ull);
             }
         }
 
@@ -156,49 +183,46 @@ __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, 
         for (int u = 0; u < kUnroll; ++u) {
             const uint32_t c = base + (uint32_t)u * 32u + lane;
             uint4 data = own[u];
-            if (!kCoAligned) {
-                uint4 nx;
-                nx.x = __shfl_down_sync(0xFFFFFFFFu, own[u].x, 1);
-                nx.y = __shfl_down_sync(0xFFFFFFFFu, own[u].y, 1);
-                nx.z = __shfl_down_sync(0xFFFFFFFFu, own[u].z, 1);
-                nx.w = __shfl_down_sync(0xFFFFFFFFu, own[u].w, 1);
-                if (lane == 31u || c + 1u >= m_hi)
-                    nx = nbr[u];
-                uint32_t w0 = own[u].x, w1 = own[u].y, w2 = own[u].z, w3 = own[u].w;
-                uint32_t w4 = nx.x, w5 = nx.y, w6 = nx.z, w7 = nx.w;
-                if (ws & 2u) {
-                    w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = w6; w5 = w7;
-                }
-                if (ws & 1u) {
-                    w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5;
-                }
-                data.x = __funnelshift_r(w0, w1, bs);
-                data.y = __funnelshift_r(w1, w2, bs);
-                data.z = __funnelshift_r(w2, w3, bs);
-                data.w = __funnelshift_r(w3, w4, bs);
+            if (kWs >= 0) {
+                const uint32_t w[8] = {own[u].x, own[u].y, own[u].z, own[u].w,
+                                       nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
+                constexpr int k = kWs < 0 ? 0 : kWs;
+                data.x = __funnelshift_r(w[k + 0], w[k + 1], bs);
+                data.y = __funnelshift_r(w[k + 1], w[k + 2], bs);
+                data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
+                data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
             }
             if (fast[u])
-                stg128(g.dst_al + 16ull * c, cycle_chunk(data, v));
+                stg128(g.dst_al + 16ull * c, cycle_chunk(data, v, two));
             v = mulmod(v, kRoundJump);  // state just before this lane's chunk of the next round
         }
     }
 }
 
-__device__ __forceinline__ void run_tile(const BatchArgs& a, const DevDesc& d, const uint32_t tile,
+// (negated) state just before byte (16 * tin * kChunksPerTile - h0) of an entry:
+//   n0 * a^(-h0) * a^(kTileBytes * tin)
+__device__ __forceinline__ uint32_t tile_start_state(int32_t key, uint32_t h0, uint32_t tin)
+{
+    uint32_t st = modlcg::key_to_neg_state(key);
+    st = mulmod(st, c_ainv[h0]);
+    return mulmod(st, mulmod(c_tw0[tin & (uint32_t)(kTw0Size - 1)], c_tw1[tin / (uint32_t)kTw0Size]));
+}
+
+__device__ __forceinline__ void run_tile(const BatchArgs& a, const uint64_t src_off, const uint64_t dst_off,
+                                         const uint32_t len, const uint32_t st, const uint32_t tin,
                                          const uint32_t lane)
 {
     TileGeom g;
-    const uint32_t tin = tile - d.first_tile;  // tile index inside the entry
-    g.len = d.len;
-    g.dst_addr = (uint64_t)a.dst + d.dst_off;
-    g.src_addr = (uint64_t)a.src + d.src_off;
+    g.len = len;
+    g.dst_addr = (uint64_t)a.dst + dst_off;
+    g.src_addr = (uint64_t)a.src + src_off;
     g.h0 = (uint32_t)g.dst_addr & 15u;
     g.dst_al = g.dst_addr - g.h0;
     const uint64_t sv = g.src_addr - g.h0;  // source address that pairs with chunk 0, byte 0
     g.shift = (uint32_t)sv & 15u;
     g.src_al = sv - g.shift;
 
-    const uint64_t span = (uint64_t)g.h0 + d.len;  // bytes from the chunk grid origin to the entry end
+    const uint64_t span = (uint64_t)g.h0 + len;  // bytes from the chunk grid origin to the entry end
     const uint32_t nchunks = (uint32_t)((span + 15u) >> 4);
     g.c_begin = tin * (uint32_t)kChunksPerTile;
     g.c_end = min(g.c_begin + (uint32_t)kChunksPerTile, nchunks);
@@ -216,12 +240,6 @@ __device__ __forceinline__ void run_tile(const BatchArgs& a, const DevDesc& d, c
     g.f_lo = (uint32_t)f_lo;
     g.f_hi = (uint32_t)f_hi;
 
-    // (negated) state just before byte (16*c_begin - h0) of the entry:
-    //   n0 * a^(-h0) * a^(kTileBytes * tin);   chunk c of the tile is a^(16*(c - c_begin)) further on
-    uint32_t st = modlcg::key_to_neg_state(d.key);
-    st = mulmod(st, c_ainv[g.h0]);
-    st = mulmod(st, mulmod(c_tw0[tin & (uint32_t)(kTw0Size - 1)], c_tw1[tin / (uint32_t)kTw0Size]));
-
     // edge chunks first (rare: skipped for tiles that are interior throughout)
     if (g.c_begin < g.f_lo || g.c_end > g.f_hi) {
         for (uint32_t c = g.c_begin + lane; c < g.c_end; c += 32u) {
@@ -229,65 +247,90 @@ __device__ __forceinline__ void run_tile(const BatchArgs& a, const DevDesc& d, c
                 continue;
             edge_chunk(reinterpret_cast<const uint8_t*>(g.src_addr), reinterpret_cast<uint8_t*>(g.dst_addr),
                        16ll * (long long)c - (long long)g.h0, g.len,
-                       mulmod(st, g_chunk_pow[c - g.c_begin]));
+                       mulmod(st, g_chunk_pow[c - g.c_begin]), a.two);
         }
     }
 
     const uint32_t v = mulmod(st, g_chunk_pow[lane]);
-    if (g.shift == 0u)
-        process_interior<true>(g, v, lane);
-    else
-        process_interior<false>(g, v, lane);
+    if (g.shift == 0u) {
+        process_interior<-1>(g, v, lane, a.two);
+    } else {
+        switch (g.shift >> 2) {
+        case 0: process_interior<0>(g, v, lane, a.two); break;
+        case 1: process_interior<1>(g, v, lane, a.two); break;
+        case 2: process_interior<2>(g, v, lane, a.two); break;
+        default: process_interior<3>(g, v, lane, a.two); break;
+        }
+    }
 }
 
-__device__ __forceinline__ DevDesc load_desc(const DevDesc* p)
+__device__ __forceinline__ TileRec load_tile_rec(const TileRec* p)
 {
-    const uint4 lo = reinterpret_cast<const uint4*>(p)[0];
-    const uint4 hi = reinterpret_cast<const uint4*>(p)[1];
-    DevDesc d;
-    d.src_off = (uint64_t)lo.x | ((uint64_t)lo.y << 32);
-    d.dst_off = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
-    d.len = hi.x;
-    d.key = (int32_t)hi.y;
-    d.first_tile = hi.z;
-    d.pad = hi.w;
-    return d;
+    const uint4 lo = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+    TileRec r;
+    r.src_off = (uint64_t)lo.x | ((uint64_t)lo.y << 32);
+    r.dst_off = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
+    r.len = hi.x;
+    r.state = hi.y;
+    r.tin = hi.z;
+    r.pad = hi.w;
+    return r;
 }
 
-__global__ void __launch_bounds__(kThreadsPerCta) cycle_batch_kernel(const BatchArgs a)
+// Persistent batched kernel: warp w of the grid takes tiles w, w + W, w + 2W, ... and loads the
+// record of its next tile before it starts streaming the current one.
+__global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_kernel(const BatchArgs a)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t tile = blockIdx.x * (uint32_t)kWarpsPerCta + (threadIdx.x >> 5);
+    const uint32_t stride = gridDim.x * (uint32_t)kWarpsPerCta;
+    uint32_t tile = blockIdx.x * (uint32_t)kWarpsPerCta + (threadIdx.x >> 5);
     if (tile >= a.n_tiles)
         return;
-    const uint32_t e = a.tile_entry ? a.tile_entry[tile] : tile / a.tiles_per_entry;
-    const DevDesc d = load_desc(a.descs + e);
-    run_tile(a, d, tile, lane);
+    TileRec cur = load_tile_rec(a.tiles + tile);
+    for (;;) {
+        const bool more = (a.n_tiles - tile) > stride;
+        TileRec nxt = cur;
+        if (more)
+            nxt = load_tile_rec(a.tiles + tile + stride);
+        run_tile(a, cur.src_off, cur.dst_off, cur.len, cur.state, cur.tin, lane);
+        if (!more)
+            break;
+        cur = nxt;
+        tile += stride;
+    }
 }
 
 // Same kernel with the (few) descriptors in the parameter block: nothing to upload, nothing to
-// allocate, so a contiguous Cycle() is a single asynchronous launch.
-__global__ void __launch_bounds__(kThreadsPerCta)
+// allocate, so a contiguous Cycle() is a single asynchronous launch.  The per-tile state comes
+// from the constant-bank jump tables instead of a tile record.
+__global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS)
 cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
 {
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t tile = blockIdx.x * (uint32_t)kWarpsPerCta + (threadIdx.x >> 5);
-    if (tile >= a.n_tiles)
-        return;
-    const uint32_t e = tile / a.tiles_per_entry;
-    const DevDesc d = in.d[e];
-    run_tile(a, d, tile, lane);
+    const uint32_t stride = gridDim.x * (uint32_t)kWarpsPerCta;
+    for (uint32_t tile = blockIdx.x * (uint32_t)kWarpsPerCta + (threadIdx.x >> 5); tile < a.n_tiles;) {
+        const uint32_t e = tile / a.tiles_per_entry;
+        const DevDesc& d = in.d[e];
+        const uint32_t tin = tile - d.first_tile;
+        const uint32_t h0 = (uint32_t)((uint64_t)a.dst + d.dst_off) & 15u;
+        run_tile(a, d.src_off, d.dst_off, d.len, tile_start_state(d.key, h0, tin), tin, lane);
+        if ((a.n_tiles - tile) <= stride)
+            break;
+        tile += stride;
+    }
 }
 
-// tile -> entry map: the last entry whose first_tile <= tile (entries with no tiles share their
-// successor's first_tile and are skipped by taking the last).
-__global__ void fill_tile_map_kernel(const DevDesc* __restrict__ descs, uint32_t n_descs,
-                                     uint32_t* __restrict__ tile_entry, uint32_t n_tiles)
+// Plan kernel, one thread per tile: find the tile's entry (the last entry whose first_tile <= tile;
+// entries with no tiles share their successor's first_tile and are skipped by taking the last) and
+// write the tile record, jump-ahead state included.
+__global__ void build_tiles_kernel(const DevDesc* __restrict__ descs, uint32_t n_descs, uint32_t dst_align,
+                                   TileRec* __restrict__ tiles, uint32_t n_tiles)
 {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles)
         return;
-    uint32_t lo = 0, hi = n_descs;  // invariant: first_tile[lo] <= t, first_tile[hi] > t (hi == n: sentinel)
+    uint32_t lo = 0, hi = n_descs;  // invariant: first_tile[lo] <= t < first_tile[hi] (hi == n: sentinel)
     while (hi - lo > 1) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
         if (descs[mid].first_tile <= t)
@@ -295,7 +338,15 @@ __global__ void fill_tile_map_kernel(const DevDesc* __restrict__ descs, uint32_t
         else
             hi = mid;
     }
-    tile_entry[t] = lo;
+    const DevDesc d = descs[lo];
+    TileRec r;
+    r.src_off = d.src_off;
+    r.dst_off = d.dst_off;
+    r.len = d.len;
+    r.tin = t - d.first_tile;
+    r.state = tile_start_state(d.key, (uint32_t)((dst_align + d.dst_off) & 15u), r.tin);
+    r.pad = lo;
+    tiles[t] = r;
 }
 
 // ---- host side --------------------------------------------------------------------------------------
@@ -323,16 +374,47 @@ cudaError_t upload_tables()
     return cudaSuccess;
 }
 
-static inline unsigned grid_for_tiles(uint32_t n_tiles)
+cudaError_t persistent_grid(int* grid_out)
 {
-    return (unsigned)((n_tiles + (uint32_t)kWarpsPerCta - 1u) / (uint32_t)kWarpsPerCta);
+    static int cached[64] = {};
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess)
+        return err;
+    if (dev < 0 || dev >= 64)
+        return cudaErrorInvalidDevice;
+    if (cached[dev] == 0) {
+        int sms = 0, per_sm_a = 0, per_sm_b = 0;
+        if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
+        if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, cycle_batch_kernel, kThreadsPerCta, 0)) != cudaSuccess) return err;
+        if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, cycle_inline_kernel, kThreadsPerCta, 0)) != cudaSuccess) return err;
+        const int per_sm = per_sm_a < per_sm_b ? per_sm_a : per_sm_b;
+        cached[dev] = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    *grid_out = cached[dev];
+    return cudaSuccess;
+}
+
+static cudaError_t grid_for_tiles(uint32_t n_tiles, unsigned* grid)
+{
+    int cap = 0;
+    cudaError_t err = persistent_grid(&cap);
+    if (err != cudaSuccess)
+        return err;
+    const unsigned want = (unsigned)((n_tiles + (uint32_t)kWarpsPerCta - 1u) / (uint32_t)kWarpsPerCta);
+    *grid = want < (unsigned)cap ? want : (unsigned)cap;
+    return cudaSuccess;
 }
 
 cudaError_t launch_batch(const BatchArgs& args, cudaStream_t stream)
 {
     if (args.n_tiles == 0)
         return cudaSuccess;
-    cycle_batch_kernel<<<grid_for_tiles(args.n_tiles), kThreadsPerCta, 0, stream>>>(args);
+    unsigned grid = 0;
+    cudaError_t err = grid_for_tiles(args.n_tiles, &grid);
+    if (err != cudaSuccess)
+        return err;
+    cycle_batch_kernel<<<grid, kThreadsPerCta, 0, stream>>>(args);
     return cudaGetLastError();
 }
 
@@ -340,18 +422,22 @@ cudaError_t launch_batch_inline(const BatchArgs& args, const InlineDescs& descs,
 {
     if (args.n_tiles == 0)
         return cudaSuccess;
-    cycle_inline_kernel<<<grid_for_tiles(args.n_tiles), kThreadsPerCta, 0, stream>>>(args, descs);
+    unsigned grid = 0;
+    cudaError_t err = grid_for_tiles(args.n_tiles, &grid);
+    if (err != cudaSuccess)
+        return err;
+    cycle_inline_kernel<<<grid, kThreadsPerCta, 0, stream>>>(args, descs);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fill_tile_map(const DevDesc* descs, uint32_t n_descs, uint32_t* tile_entry,
-                                 uint32_t n_tiles, cudaStream_t stream)
+cudaError_t launch_build_tiles(const DevDesc* descs, uint32_t n_descs, uint32_t dst_align, TileRec* tiles,
+                               uint32_t n_tiles, cudaStream_t stream)
 {
     if (n_tiles == 0)
         return cudaSuccess;
     const unsigned threads = 256;
-    fill_tile_map_kernel<<<(n_tiles + threads - 1) / threads, threads, 0, stream>>>(descs, n_descs,
-                                                                                    tile_entry, n_tiles);
+    build_tiles_kernel<<<(n_tiles + threads - 1) / threads, threads, 0, stream>>>(descs, n_descs, dst_align,
+                                                                                 tiles, n_tiles);
     return cudaGetLastError();
 }
 

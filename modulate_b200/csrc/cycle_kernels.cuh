@@ -7,21 +7,37 @@
 namespace modk {
 
 // Geometry of the work decomposition.  A "chunk" is one 16-byte, 16-byte-aligned piece of the
-// DESTINATION address space; a "tile" is what one warp processes: kIters rounds of 32 chunks.
-constexpr int kIters = 8;
+// DESTINATION address space; a "tile" is what one warp processes at a time: kIters rounds of 32
+// chunks (4 KiB of destination).
+#ifndef MODK_ITERS
+#define MODK_ITERS 8
+#endif
+constexpr int kIters = MODK_ITERS;
 constexpr int kChunksPerTile = 32 * kIters;           // 256 chunks
-constexpr uint32_t kTileBytes = 16u * kChunksPerTile;  // 4 KiB of destination per warp
+constexpr uint32_t kTileBytes = 16u * kChunksPerTile;  // 4 KiB of destination per tile
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreadsPerCta = 32 * kWarpsPerCta;
 constexpr int kMaxInlineDescs = 64;  // descriptors that travel in the kernel parameter block
 
-// Device-side descriptor: mod_desc plus the index of the entry's first tile (32 bytes, two LDG.128).
+// Device-side descriptor: mod_desc plus the index of the entry's first tile (32 bytes).
 struct __align__(16) DevDesc {
     uint64_t src_off;
     uint64_t dst_off;
     uint32_t len;
     int32_t key;
     uint32_t first_tile;
+    uint32_t pad;
+};
+
+// One record per tile, written once by the plan kernel and read (one 32-byte load, prefetched a
+// tile ahead) by the batched kernel: everything a warp needs to start streaming, so the hot kernel
+// does no search, no division and no table walk.
+struct __align__(16) TileRec {
+    uint64_t src_off;  // of the ENTRY this tile belongs to
+    uint64_t dst_off;
+    uint32_t len;      // entry length
+    uint32_t state;    // negated LCG state just before byte (16 * c_begin - h0) of the entry
+    uint32_t tin;      // tile index inside the entry (c_begin = tin * kChunksPerTile)
     uint32_t pad;
 };
 
@@ -32,13 +48,13 @@ struct InlineDescs {
 struct BatchArgs {
     const uint8_t* src;
     uint8_t* dst;
-    const DevDesc* descs;        // HBM descriptors (nullptr in inline mode)
-    const uint32_t* tile_entry;  // tile -> entry map (nullptr: entry = tile / tiles_per_entry)
+    const TileRec* tiles;  // HBM tile records (nullptr in inline mode)
     uint32_t n_tiles;
-    uint32_t tiles_per_entry;
+    uint32_t tiles_per_entry;  // inline mode: entry = tile / tiles_per_entry
     // 16-byte granules of the source may be loaded whole only inside [src_lo16, src_hi16).
     uint64_t src_lo16;
     uint64_t src_hi16;
+    uint32_t two = 2;  // the literal 2, kept opaque to ptxas (see low8_canonical_fma)
 };
 
 // Number of tiles an entry of `len` bytes occupies when its first destination byte sits at
@@ -51,10 +67,13 @@ __host__ __device__ inline uint32_t tiles_for_entry(uint32_t h0, uint32_t len)
     return (uint32_t)((chunks + kChunksPerTile - 1) / kChunksPerTile);
 }
 
-cudaError_t upload_tables();  // jump tables -> __constant__ memory of the current device
+cudaError_t upload_tables();  // jump tables -> __constant__ / global memory of the current device
+// Persistent grid size for the current device (SM count x resident CTAs per SM), cached per device.
+cudaError_t persistent_grid(int* grid_out);
 cudaError_t launch_batch(const BatchArgs& args, cudaStream_t stream);
 cudaError_t launch_batch_inline(const BatchArgs& args, const InlineDescs& descs, cudaStream_t stream);
-cudaError_t launch_fill_tile_map(const DevDesc* descs, uint32_t n_descs, uint32_t* tile_entry,
-                                 uint32_t n_tiles, cudaStream_t stream);
+// Plan kernel: expands descriptors into per-tile records (binary search + jump-ahead per tile).
+cudaError_t launch_build_tiles(const DevDesc* descs, uint32_t n_descs, uint32_t dst_align, TileRec* tiles,
+                               uint32_t n_tiles, cudaStream_t stream);
 
 }  // namespace modk

@@ -192,8 +192,7 @@ int launch_contiguous(const uint8_t* d_src, uint8_t* d_dst, uint64_t len, int32_
         }
         args.src = d_src + group_base;
         args.dst = d_dst + group_base;
-        args.descs = nullptr;
-        args.tile_entry = nullptr;
+        args.tiles = nullptr;
         args.n_tiles = tiles;
         args.tiles_per_entry = tpe;
         args.src_lo16 = src_lo16;
@@ -214,8 +213,7 @@ struct mod_plan {
     uint32_t dst_align = 0;
     uint64_t payload = 0;
     uint32_t n_tiles = 0;
-    modk::DevDesc* d_descs = nullptr;
-    uint32_t* d_tile_entry = nullptr;
+    modk::TileRec* d_tiles = nullptr;
 };
 
 extern "C" {
@@ -440,23 +438,24 @@ int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint6
     p->dst_align = dst_align;
     p->payload = payload;
     p->n_tiles = (uint32_t)tiles;
+    modk::DevDesc* d_descs = nullptr;  // only needed while the tile records are built
     auto cleanup = [&]() {
-        if (p->d_descs) cudaFree(p->d_descs);
-        if (p->d_tile_entry) cudaFree(p->d_tile_entry);
+        if (d_descs) cudaFree(d_descs);
+        if (p->d_tiles) cudaFree(p->d_tiles);
         delete p;
     };
-    if (n) {
-        cudaError_t e = cudaMalloc((void**)&p->d_descs, n * sizeof(modk::DevDesc));
-        if (e == cudaSuccess && tiles)
-            e = cudaMalloc((void**)&p->d_tile_entry, tiles * sizeof(uint32_t));
+    if (n && tiles) {
+        cudaError_t e = cudaMalloc((void**)&d_descs, n * sizeof(modk::DevDesc));
+        if (e == cudaSuccess)
+            e = cudaMalloc((void**)&p->d_tiles, tiles * sizeof(modk::TileRec));
         if (e != cudaSuccess) {
             cudaGetLastError();
             cleanup();
             return fail(MOD_ERR_NOMEM, "mod_plan_create: cudaMalloc failed: %s", cudaGetErrorString(e));
         }
-        e = cudaMemcpy(p->d_descs, host.data(), n * sizeof(modk::DevDesc), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess && tiles) {
-            e = modk::launch_fill_tile_map(p->d_descs, (uint32_t)n, p->d_tile_entry, p->n_tiles, nullptr);
+        e = cudaMemcpy(d_descs, host.data(), n * sizeof(modk::DevDesc), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            e = modk::launch_build_tiles(d_descs, (uint32_t)n, dst_align, p->d_tiles, p->n_tiles, nullptr);
             g_launches.fetch_add(1, std::memory_order_relaxed);
         }
         if (e == cudaSuccess)
@@ -465,6 +464,8 @@ int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint6
             cleanup();
             return fail(MOD_ERR_CUDA, "mod_plan_create: %s", cudaGetErrorString(e));
         }
+        cudaFree(d_descs);
+        d_descs = nullptr;
     }
     *out = p;
     return MOD_OK;
@@ -474,10 +475,8 @@ int mod_plan_destroy(mod_plan* plan)
 {
     if (!plan)
         return MOD_OK;
-    if (plan->d_descs)
-        cudaFree(plan->d_descs);
-    if (plan->d_tile_entry)
-        cudaFree(plan->d_tile_entry);
+    if (plan->d_tiles)
+        cudaFree(plan->d_tiles);
     delete plan;
     return MOD_OK;
 }
@@ -499,8 +498,7 @@ int mod_plan_run(const mod_plan* plan, const void* d_src, void* d_dst, void* str
     modk::BatchArgs args;
     args.src = (const uint8_t*)d_src;
     args.dst = (uint8_t*)d_dst;
-    args.descs = plan->d_descs;
-    args.tile_entry = plan->d_tile_entry;
+    args.tiles = plan->d_tiles;
     args.n_tiles = plan->n_tiles;
     args.tiles_per_entry = 0;
     args.src_lo16 = ((uint64_t)(uintptr_t)d_src + 15u) & ~15ull;
