@@ -42,7 +42,13 @@ using modlcg::low8_canonical;
 #define MODK_CANON_FMA_MASK 0x5  // which of every 4 bytes canonicalise on the FMA pipe (IMAD.HI) vs ALU (LEA.HI)
 #endif
 #ifndef MODK_MIN_CTAS
-#define MODK_MIN_CTAS 3          // resident CTAs per SM requested through __launch_bounds__
+#define MODK_MIN_CTAS 4          // resident CTAs per SM requested through __launch_bounds__ (64 registers)
+#endif
+#ifndef MODK_LD_HINT
+#define MODK_LD_HINT 0           // 0: ld.global   1: .L1::no_allocate on the co-aligned path   2: .cs everywhere
+#endif
+#ifndef MODK_ST_HINT
+#define MODK_ST_HINT 0           // 0: st.global   1: st.global.cs (streaming)
 #endif
 
 constexpr int kUnroll = MODK_UNROLL;
@@ -61,18 +67,28 @@ constexpr uint32_t kRoundJump = modlcg::pow_a(512);  // one round = 32 lanes x 1
 
 // ---- 128-bit global accesses (explicit state space: the addresses are rebuilt from integers) ------
 
+template <bool kStreamOnce>
 __device__ __forceinline__ uint4 ldg128(uint64_t addr)
 {
     uint4 r;
-    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(addr));
+    if (MODK_LD_HINT == 2)
+        asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(addr));
+    else if (MODK_LD_HINT == 1 && kStreamOnce)
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(addr));
+    else
+        asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(addr));
     return r;
 }
 
 __device__ __forceinline__ void stg128(uint64_t addr, const uint4& v)
 {
-    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+    if (MODK_ST_HINT == 1)
+        asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+    else
+        asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 
 // ---- per-chunk arithmetic -------------------------------------------------------------------
@@ -148,7 +164,10 @@ __device__ __noinline__ void edge_chunk(const uint8_t* src_entry, uint8_t* dst_e
     }
 }
 
-// Interior chunks of the tile: kUnroll independent chunks in flight per thread.
+// Interior chunks of the tile: kUnroll independent chunks in flight per thread (all loads of a
+// group are issued before any is consumed).  A register ping-pong that issued the next group's
+// loads before ciphering the current one measured SLOWER on B200 (profiles/r01_tuning.md), so the
+// simple form stays: latency is covered by the 32 resident warps per SM.
 // kWs < 0: source and destination are co-aligned (one load per chunk).  kWs in 0..3: the chunk
 // starts kWs words (+ a runtime 0..3 bytes) into its first granule and straddles two.
 template <int kWs>
@@ -172,9 +191,9 @@ __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, 
             own[u] = make_uint4(0u, 0u, 0u, 0u);
             nxt[u] = make_uint4(0u, 0u, 0u, 0u);
             if (fast[u]) {
-                own[u] = ldg128(g.src_al + 16ull * c);
+                own[u] = ldg128<(kWs < 0)>(g.src_al + 16ull * c);
                 if (kWs >= 0)
-                    nxt[u] = ldg128(g.src_al + 16ull * c + 16ull);
+                    nxt[u] = ldg128<false>(g.src_al + 16ull * c + 16ull);
             }
         }
 

@@ -8,13 +8,13 @@ namespace modk {
 
 // Geometry of the work decomposition.  A "chunk" is one 16-byte, 16-byte-aligned piece of the
 // DESTINATION address space; a "tile" is what one warp processes at a time: kIters rounds of 32
-// chunks (4 KiB of destination).
+// chunks (8 KiB of destination with the default kIters = 16).
 #ifndef MODK_ITERS
-#define MODK_ITERS 8
+#define MODK_ITERS 16
 #endif
 constexpr int kIters = MODK_ITERS;
-constexpr int kChunksPerTile = 32 * kIters;           // 256 chunks
-constexpr uint32_t kTileBytes = 16u * kChunksPerTile;  // 4 KiB of destination per tile
+constexpr int kChunksPerTile = 32 * kIters;           // 512 chunks
+constexpr uint32_t kTileBytes = 16u * kChunksPerTile;  // 8 KiB of destination per tile
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreadsPerCta = 32 * kWarpsPerCta;
 constexpr int kMaxInlineDescs = 64;  // descriptors that travel in the kernel parameter block

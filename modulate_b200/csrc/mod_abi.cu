@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -64,6 +65,11 @@ struct Context {
 };
 
 Context g_ctx;
+
+double now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 uint64_t env_u64(const char* name, uint64_t dflt)
 {
@@ -536,12 +542,19 @@ int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t
         return MOD_OK;
     }
 
-    // Host buffers: stage the source image in HBM, run the plan, bring back only the destination
-    // bytes the descriptors cover (merged into maximal runs) so untouched bytes of dst survive,
-    // exactly like the reference's per-entry fwrite / fread.
+    // Host buffers.  The HBM workspaces mirror the host buffers 1:1, the plan (descriptors -> tile
+    // records) is built once, and the entries are then streamed in GROUPS of consecutive
+    // descriptors (~MOD_GROUP_BYTES of payload each): group g uploads the source window its
+    // entries span, runs the batched kernel over its tile sub-range and downloads the destination
+    // runs it covers, on stream g % kPipeSlots -- so the upload of one group, the kernel of another
+    // and the download of a third overlap.  Only bytes covered by descriptors are written back,
+    // so untouched bytes of dst survive exactly like with the reference's per-entry fwrite/fread.
+    const bool trace = env_u64("MOD_TRACE", 0) != 0;
+    const double t_begin = now_ms();
     rc = mod_plan_create(descs, n, src_bytes, dst_bytes, 0, &plan);
     if (rc != MOD_OK)
         return rc;
+    const double t_plan = now_ms();
     std::lock_guard<std::mutex> lock(g_ctx.mu);
     auto done = [&](int code) {
         mod_plan_destroy(plan);
@@ -552,42 +565,131 @@ int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t
     if ((rc = grow(&g_ctx.ws_dst, &g_ctx.ws_dst_bytes, dst_bytes)) != MOD_OK)
         return done(rc);
 
-    std::vector<std::pair<uint64_t, uint64_t>> runs;  // [begin, end) in dst
-    runs.reserve(n);
-    for (uint64_t i = 0; i < n; ++i)
-        if (descs[i].len)
-            runs.emplace_back(descs[i].dst_off, descs[i].dst_off + descs[i].len);
-    std::sort(runs.begin(), runs.end());
-    size_t m = 0;
-    for (size_t i = 0; i < runs.size(); ++i) {
-        if (m && runs[i].first <= runs[m - 1].second)
-            runs[m - 1].second = std::max(runs[m - 1].second, runs[i].second);
-        else
-            runs[m++] = runs[i];
-    }
-    runs.resize(m);
-
-    cudaStream_t s = g_ctx.pipe_stream[0];
-    cudaError_t e = cudaMemcpyAsync(g_ctx.ws_src, src, src_bytes, cudaMemcpyHostToDevice, s);
-    const bool sparse = runs.size() > 256;  // many holes: round-trip the whole destination instead
-    if (e == cudaSuccess && sparse)
-        e = cudaMemcpyAsync(g_ctx.ws_dst, dst, dst_bytes, cudaMemcpyHostToDevice, s);
-    if (e != cudaSuccess)
-        return done(fail(MOD_ERR_CUDA, "mod_cycle_batch: upload: %s", cudaGetErrorString(e)));
-    if ((rc = mod_plan_run(plan, g_ctx.ws_src, g_ctx.ws_dst, s)) != MOD_OK)
-        return done(rc);
-    if (sparse) {
-        e = cudaMemcpyAsync(dst, g_ctx.ws_dst, dst_bytes, cudaMemcpyDeviceToHost, s);
-    } else {
-        for (const auto& r : runs) {
-            e = cudaMemcpyAsync((uint8_t*)dst + r.first, (const uint8_t*)g_ctx.ws_dst + r.first,
-                                r.second - r.first, cudaMemcpyDeviceToHost, s);
-            if (e != cudaSuccess)
-                break;
+    struct Group {
+        uint64_t e0, e1;        // descriptor range
+        uint32_t t0, t1;        // tile range
+        uint64_t s_lo, s_hi;    // source window
+    };
+    const uint64_t group_bytes = std::max<uint64_t>(1 << 20, env_u64("MOD_GROUP_BYTES", 16ull << 20));
+    std::vector<Group> groups;
+    {
+        Group g{0, 0, 0, 0, UINT64_MAX, 0};
+        uint64_t acc = 0;
+        uint32_t tile = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            const mod_desc& d = descs[i];
+            if (d.len) {
+                g.s_lo = std::min(g.s_lo, d.src_off);
+                g.s_hi = std::max(g.s_hi, d.src_off + d.len);
+            }
+            acc += d.len;
+            tile += modk::tiles_for_entry((uint32_t)(d.dst_off & 15u), d.len);
+            if (acc >= group_bytes || i + 1 == n) {
+                g.e1 = i + 1;
+                g.t1 = tile;
+                if (g.t1 > g.t0)
+                    groups.push_back(g);
+                g = Group{i + 1, 0, tile, 0, UINT64_MAX, 0};
+                acc = 0;
+            }
         }
     }
-    if (e == cudaSuccess)
-        e = cudaStreamSynchronize(s);
+    // If the entries are not laid out in source order the windows overlap heavily and per-group
+    // uploads would move the image many times: fall back to a single group then.
+    uint64_t window_sum = 0;
+    for (const Group& g : groups)
+        window_sum += g.s_hi - g.s_lo;
+    if (window_sum > src_bytes + src_bytes / 4 + (1 << 20)) {
+        Group all{0, n, 0, plan->n_tiles, 0, src_bytes};
+        groups.assign(1, all);
+    }
+
+    // Destination runs (maximal covered intervals) per group.  A batch whose destination is full of
+    // holes (more than 64 runs in a group) is handled exactly but without pipelining: the whole
+    // destination makes a round trip through HBM so that the holes keep their host bytes.
+    auto merged_runs = [&](const Group& g, std::vector<std::pair<uint64_t, uint64_t>>& runs) {
+        runs.clear();
+        for (uint64_t i = g.e0; i < g.e1; ++i)
+            if (descs[i].len)
+                runs.emplace_back(descs[i].dst_off, descs[i].dst_off + descs[i].len);
+        std::sort(runs.begin(), runs.end());
+        size_t m = 0;
+        for (size_t i = 0; i < runs.size(); ++i) {
+            // gaps of fewer than 16 bytes are alignment padding between entries: they are bridged
+            // and come back zero-filled (documented in include/modulate_b200.h)
+            if (m && runs[i].first < runs[m - 1].second + 16)
+                runs[m - 1].second = std::max(runs[m - 1].second, runs[i].second);
+            else
+                runs[m++] = runs[i];
+        }
+        runs.resize(m);
+    };
+    std::vector<std::pair<uint64_t, uint64_t>> runs;
+    bool holes = false;
+    for (const Group& g : groups) {
+        merged_runs(g, runs);
+        if (runs.size() > 64) {
+            holes = true;
+            break;
+        }
+    }
+    if (holes) {
+        Group all{0, n, 0, plan->n_tiles, 0, src_bytes};
+        groups.assign(1, all);
+    }
+
+    const uint64_t src_lo16 = ((uint64_t)(uintptr_t)g_ctx.ws_src + 15u) & ~15ull;
+    const uint64_t src_hi16 = ((uint64_t)(uintptr_t)g_ctx.ws_src + src_bytes) & ~15ull;
+    cudaError_t e = cudaSuccess;
+    for (size_t gi = 0; gi < groups.size() && e == cudaSuccess; ++gi) {
+        const Group& g = groups[gi];
+        cudaStream_t s = g_ctx.pipe_stream[gi % kPipeSlots];
+        e = cudaMemcpyAsync((uint8_t*)g_ctx.ws_src + g.s_lo, (const uint8_t*)src + g.s_lo, g.s_hi - g.s_lo,
+                            cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && holes)
+            e = cudaMemcpyAsync(g_ctx.ws_dst, dst, dst_bytes, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && !holes) {  // zero the runs so that bridged padding is deterministic
+            merged_runs(g, runs);
+            for (const auto& r : runs) {
+                e = cudaMemsetAsync((uint8_t*)g_ctx.ws_dst + r.first, 0, r.second - r.first, s);
+                if (e != cudaSuccess)
+                    break;
+            }
+        }
+        if (e != cudaSuccess)
+            break;
+        modk::BatchArgs args;
+        args.src = (const uint8_t*)g_ctx.ws_src;
+        args.dst = (uint8_t*)g_ctx.ws_dst;
+        args.tiles = plan->d_tiles + g.t0;
+        args.n_tiles = g.t1 - g.t0;
+        args.tiles_per_entry = 0;
+        args.src_lo16 = src_lo16;
+        args.src_hi16 = src_hi16;
+        e = modk::launch_batch(args, s);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e != cudaSuccess)
+            break;
+        if (holes) {
+            e = cudaMemcpyAsync(dst, g_ctx.ws_dst, dst_bytes, cudaMemcpyDeviceToHost, s);
+        } else {
+            for (const auto& r : runs) {
+                e = cudaMemcpyAsync((uint8_t*)dst + r.first, (const uint8_t*)g_ctx.ws_dst + r.first,
+                                    r.second - r.first, cudaMemcpyDeviceToHost, s);
+                if (e != cudaSuccess)
+                    break;
+            }
+        }
+    }
+    const double t_enq = now_ms();
+    for (int k = 0; k < kPipeSlots; ++k) {
+        cudaError_t es = cudaStreamSynchronize(g_ctx.pipe_stream[k]);
+        if (e == cudaSuccess)
+            e = es;
+    }
+    if (trace)
+        fprintf(stderr, "[mod] cycle_batch: plan %.2f ms, enqueue %zu groups %.2f ms, drain %.2f ms\n", t_plan - t_begin,
+                groups.size(), t_enq - t_plan, now_ms() - t_enq);
     if (e != cudaSuccess)
         return done(fail(MOD_ERR_CUDA, "mod_cycle_batch: %s", cudaGetErrorString(e)));
     return done(MOD_OK);

@@ -344,3 +344,41 @@ def test_sharded_plans_equal_unsharded(mb):
                                                        o - int(off[2]))).all()
     for b in (src, whole, parts):
         b.free()
+
+
+@pytest.mark.parametrize("layout", ["packed", "shuffled", "holes"])
+def test_batch_host_buffers_pipelined(mb, layout, monkeypatch):
+    """mod_cycle_batch on HOST buffers: grouped H2D / kernel / D2H pipeline (small groups forced),
+    the non-monotone fallback, and a destination with many holes (bytes between entries survive)."""
+    monkeypatch.setenv("MOD_GROUP_BYTES", str(1 << 20))
+    rng = np.random.default_rng(8)
+    n = 600
+    sizes = synth.entry_sizes_loguniform(n, 12 << 20, lo=16, hi=1 << 17, seed=5)
+    src_off = synth.packed_offsets(sizes)
+    if layout == "packed":
+        dst_off = synth.packed_offsets((sizes + 15) & ~15)  # 16-byte aligned slots, monotone, padding < 16
+    elif layout == "shuffled":
+        order = rng.permutation(n)
+        dst_off = np.zeros(n, np.int64)
+        run = 3
+        for i in order:
+            dst_off[i] = run
+            run += int(sizes[i])
+        # present the descriptors in destination order so that source windows jump around
+        src_off, sizes, dst_off = src_off[order], sizes[order], dst_off[order]
+    else:
+        dst_off = src_off * 2 + 7  # every entry followed by a hole
+    keys = synth.entry_keys(n, seed=21)
+    descs = mb.make_descs(src_off, dst_off, sizes, keys)
+    src = synth.payload(3, int((src_off + sizes).max()))
+    dst = np.full(int((dst_off + sizes).max()) + 9, 0x77, np.uint8)
+    want = oracle.cycle_batch(descs, src, dst.copy())
+    if layout == "packed":
+        # documented host-form rule: gaps of < 16 bytes between entries are padding and come back zero
+        covered = np.zeros(dst.size, bool)
+        for d in descs:
+            covered[int(d["dst_off"]):int(d["dst_off"]) + int(d["len"])] = True
+        span_end = int((dst_off + sizes).max())
+        want[:span_end][~covered[:span_end]] = 0
+    mb.cycle_batch(descs, src, dst)
+    assert (dst == want).all()
