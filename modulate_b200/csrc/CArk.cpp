@@ -1,0 +1,483 @@
+#include "CArk.h"
+
+#include <dirent.h>
+#include <sys/stat.h>
+#include <sys/types.h>
+
+#include <algorithm>
+#include <cctype>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+
+#include "../../include/modulate_b200.h"
+#include "CEncryptionCycler.h"
+#include "Settings.h"
+
+namespace {
+
+bool ReadWholeFile(const std::string& lPath, std::vector<unsigned char>& lOut)
+{
+    FILE* lpFile = std::fopen(lPath.c_str(), "rb");
+    if (!lpFile)
+        return false;
+    std::fseek(lpFile, 0, SEEK_END);
+    const long liSize = std::ftell(lpFile);
+    std::fseek(lpFile, 0, SEEK_SET);
+    lOut.resize(liSize > 0 ? (size_t)liSize : 0);
+    const size_t liRead = lOut.empty() ? 0 : std::fread(lOut.data(), 1, lOut.size(), lpFile);
+    std::fclose(lpFile);
+    return liRead == lOut.size();
+}
+
+long FileSize(const std::string& lPath)
+{
+    struct stat lInfo;
+    if (stat(lPath.c_str(), &lInfo) != 0 || !S_ISREG(lInfo.st_mode))
+        return -1;
+    return (long)lInfo.st_size;
+}
+
+bool IsDirectory(const std::string& lPath)
+{
+    struct stat lInfo;
+    return stat(lPath.c_str(), &lInfo) == 0 && S_ISDIR(lInfo.st_mode);
+}
+
+// mkdir -p for every directory component of lFilePath (the part before the last '/').
+bool MakeParentDirectories(const std::string& lFilePath)
+{
+    for (size_t liSlash = lFilePath.find('/'); liSlash != std::string::npos; liSlash = lFilePath.find('/', liSlash + 1)) {
+        if (liSlash == 0)
+            continue;
+        const std::string lDir = lFilePath.substr(0, liSlash);
+        mkdir(lDir.c_str(), 0777);
+        if (!IsDirectory(lDir))
+            return false;
+    }
+    return true;
+}
+
+// Existing non-empty output is kept only when overwriting is disabled (reference CArk.cpp:439-454).
+bool KeepExistingOutput(const std::string& lPath)
+{
+    if (CSettings::mbOverwriteOutputFiles)
+        return false;
+    return FileSize(lPath) > 0;
+}
+
+// Relative names of every regular file under lRoot (which ends in '/'), files of a directory first,
+// then its sub-directories, each level in case-insensitive name order (the reference walks with
+// FindFirstFileA, Utils.cpp:5-70, whose NTFS order is alphabetical).
+void ListFiles(const std::string& lRoot, const std::string& lRelative, std::vector<std::string>& laOut)
+{
+    DIR* lpDir = opendir((lRoot + lRelative).c_str());
+    if (!lpDir)
+        return;
+    std::vector<std::string> laFiles, laDirs;
+    while (dirent* lpEntry = readdir(lpDir)) {
+        const std::string lName = lpEntry->d_name;
+        if (lName == "." || lName == "..")
+            continue;
+        const std::string lFull = lRoot + lRelative + lName;
+        if (IsDirectory(lFull))
+            laDirs.push_back(lName);
+        else if (FileSize(lFull) >= 0)
+            laFiles.push_back(lName);
+    }
+    closedir(lpDir);
+    auto lLess = [](const std::string& lA, const std::string& lB) {
+        return std::lexicographical_compare(lA.begin(), lA.end(), lB.begin(), lB.end(), [](char a, char b) {
+            return std::tolower((unsigned char)a) < std::tolower((unsigned char)b);
+        });
+    };
+    std::sort(laFiles.begin(), laFiles.end(), lLess);
+    std::sort(laDirs.begin(), laDirs.end(), lLess);
+    for (const std::string& lName : laFiles)
+        laOut.push_back(lRelative + lName);
+    for (const std::string& lName : laDirs)
+        ListFiles(lRoot, lRelative + lName + "/", laOut);
+}
+
+}  // namespace
+
+CArk::CArk() {}
+
+CArk::~CArk() { ReleaseArkData(); }
+
+void CArk::ReleaseArkData()
+{
+    if (mpArkData)
+        mod_host_free(mpArkData);
+    mpArkData = nullptr;
+    muArkDataSize = 0;
+}
+
+void CArk::SetUniformEntryKey(int liKey)
+{
+    miUniformKey = liKey;
+    maEntryKeys.clear();
+}
+
+void CArk::SetEntryKeys(const std::vector<int>& laKeys) { maEntryKeys = laKeys; }
+
+void CArk::SetPartDirectory(const char* lpDirectory)
+{
+    mPartDirectory = lpDirectory ? lpDirectory : "";
+    if (!mPartDirectory.empty() && mPartDirectory.back() != '/')
+        mPartDirectory += '/';
+}
+
+int CArk::EntryKey(size_t liIndex) const { return liIndex < maEntryKeys.size() ? maEntryKeys[liIndex] : miUniformKey; }
+
+int CArk::GetNumFiles() const { return (int)mHeader.maFiles.size(); }
+
+bool CArk::FileExists(const char* lpFilename) const
+{
+    for (const modark::FileDef& lFile : mHeader.maFiles)
+        if (lFile.mName == lpFilename)
+            return true;
+    return false;
+}
+
+// ---- read side ---------------------------------------------------------------------------------------
+
+eError CArk::Load(const char* lpHeaderFilename)
+{
+    if (mbLoaded)
+        return eError_AlreadyLoaded;  // reference CArk.cpp:303-306
+
+    VERBOSE_OUT("Loading header file " << lpHeaderFilename);
+    std::vector<unsigned char> lData;
+    if (!ReadWholeFile(lpHeaderFilename, lData))
+        return eError_FailedToOpenFile;
+    VERBOSE_OUT("\nLoaded header (" << lData.size() << ") bytes\n");
+    if (lData.size() < sizeof(uint32_t))
+        return eError_UnknownVersionNumber;
+
+    uint32_t luVersion = 0;
+    std::memcpy(&luVersion, lData.data(), sizeof(luVersion));
+    if (luVersion != CSettings::kuEncryptedVersionPS3 && luVersion != CSettings::kuEncryptedVersionPS4)
+        return eError_UnknownVersionNumber;
+    const unsigned int kuInitialKey =
+        (luVersion == CSettings::kuEncryptedVersionPS3) ? CSettings::kuEncryptedPS3Key : CSettings::kuEncryptedPS4Key;
+
+    // the magic stays in clear; everything after it is one Cycle() -- on the GPU
+    CEncryptionCycler lDecrypt;
+    lDecrypt.Cycle(lData.data() + sizeof(uint32_t), (unsigned int)(lData.size() - sizeof(uint32_t)), (int)kuInitialKey);
+
+    eError leError = modark::ParseHeader(lData.data(), lData.size(), mHeader);
+    SHOW_ERROR_AND_RETURN;
+    mbLoaded = true;
+    return eError_NoError;
+}
+
+eError CArk::LoadArkData()
+{
+    ReleaseArkData();
+    uint64_t luTotalArkSize = 0;
+    for (const modark::PartDef& lPart : mHeader.maParts)
+        luTotalArkSize += lPart.muSize;
+
+    mpArkData = (unsigned char*)mod_host_alloc(luTotalArkSize ? luTotalArkSize : 1);
+    if (!mpArkData) {
+        std::cout << "Failed to allocate pinned memory for the archive: " << mod_last_error() << "\n";
+        return eError_NoData;
+    }
+    muArkDataSize = luTotalArkSize;
+
+    unsigned char* lpArkPtr = mpArkData;
+    for (const modark::PartDef& lPart : mHeader.maParts) {
+        const std::string lPath = mPartDirectory + lPart.mPath;
+        FILE* lpArkFile = std::fopen(lPath.c_str(), "rb");
+        if (!lpArkFile) {
+            eError leError = eError_FailedToOpenFile;
+            SHOW_ERROR_AND_RETURN;
+        }
+        const size_t liRead = lPart.muSize ? std::fread(lpArkPtr, 1, lPart.muSize, lpArkFile) : 0;
+        std::fclose(lpArkFile);
+        if (liRead != lPart.muSize)
+            std::memset(lpArkPtr + liRead, 0, lPart.muSize - liRead);  // short part: the reference leaves garbage
+        lpArkPtr += lPart.muSize;
+    }
+    return eError_NoError;
+}
+
+eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTargetDirectory)
+{
+    (void)liFirstFileIndex;  // the reference ignores both and walks the whole table (CArk.cpp:435)
+    (void)liNumFiles;
+    if (mHeader.maFiles.empty())
+        return eError_NoData;
+
+    eError leError = LoadArkData();
+    SHOW_ERROR_AND_RETURN;
+
+    // file table -> device descriptors: gather every entry into a byte-packed staging buffer
+    const size_t liCount = mHeader.maFiles.size();
+    std::vector<mod_desc> laDescs(liCount);
+    uint64_t luStagingSize = 0;
+    for (size_t ii = 0; ii < liCount; ++ii) {
+        const modark::FileDef& lFile = mHeader.maFiles[ii];
+        if ((uint64_t)lFile.mi64Offset > muArkDataSize || (uint64_t)lFile.miSize > muArkDataSize - (uint64_t)lFile.mi64Offset) {
+            std::cout << "Entry " << lFile.mName.c_str() << " lies outside the archive data\n";
+            leError = eError_InvalidData;
+            SHOW_ERROR_AND_RETURN;
+        }
+        laDescs[ii].src_off = (uint64_t)lFile.mi64Offset;
+        laDescs[ii].dst_off = luStagingSize;
+        laDescs[ii].len = (uint32_t)lFile.miSize;
+        laDescs[ii].key = EntryKey(ii);
+        luStagingSize += (uint64_t)lFile.miSize;
+    }
+    unsigned char* lpStaging = (unsigned char*)mod_host_alloc(luStagingSize ? luStagingSize : 1);
+    if (!lpStaging) {
+        std::cout << "Failed to allocate pinned staging memory: " << mod_last_error() << "\n";
+        return eError_NoData;
+    }
+    if (mod_cycle_batch(laDescs.data(), liCount, mpArkData, muArkDataSize, lpStaging, luStagingSize) != MOD_OK) {
+        std::cout << "GPU extract failed: " << mod_last_error() << "\n";
+        mod_host_free(lpStaging);
+        return eError_InvalidData;
+    }
+
+    for (size_t ii = 0; ii < liCount; ++ii) {
+        const modark::FileDef& lFile = mHeader.maFiles[ii];
+        const std::string lOutputPath = std::string(lpTargetDirectory) + lFile.mName;
+        if (KeepExistingOutput(lOutputPath)) {
+            VERBOSE_OUT("Output file already exists, skipping: " << lOutputPath.c_str() << "\n");
+            continue;
+        }
+        if (!MakeParentDirectories(lOutputPath)) {
+            leError = eError_FailedToCreateDirectory;
+            SHOW_ERROR_AND_RETURN_W(mod_host_free(lpStaging));
+        }
+        VERBOSE_OUT("Writing file " << lOutputPath.c_str() << "\n");
+        FILE* lpOutputFile = std::fopen(lOutputPath.c_str(), "wb");
+        if (!lpOutputFile) {
+            std::cout << "Failed to create " << lOutputPath.c_str() << "\n";  // the reference carries on too (CArk.cpp:488-491)
+            continue;
+        }
+        const size_t liWritten = lFile.miSize ? std::fwrite(lpStaging + laDescs[ii].dst_off, 1, (size_t)lFile.miSize, lpOutputFile) : 0;
+        std::fclose(lpOutputFile);
+        if (liWritten != (size_t)lFile.miSize) {
+            mod_host_free(lpStaging);
+            return eError_FailedToWriteData;
+        }
+    }
+    mod_host_free(lpStaging);
+    return eError_NoError;
+}
+
+// ---- write side --------------------------------------------------------------------------------------
+
+bool CArk::ShouldPackFile(const std::vector<SSongConfig>& laSongs, const char* lpFilename) const
+{
+    // Files under ".../songs/<name>/" are packed only when <name> occurs in some configured song
+    // path; everything else always is (policy of the reference, CArk.cpp:58-92).
+    const char* lpSongs = std::strstr(lpFilename, "/songs/");
+    if (!lpSongs)
+        return true;
+    const char* lpEnd = lpSongs + std::strlen("/songs/");
+    while (*lpEnd && *lpEnd != '/')
+        ++lpEnd;
+    if (!*lpEnd)
+        return false;
+    std::string lSongName(lpSongs, lpEnd - lpSongs);
+    std::transform(lSongName.begin(), lSongName.end(), lSongName.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+    for (const SSongConfig& lSong : laSongs)
+        if (lSong.mPath.find(lSongName) != std::string::npos)
+            return true;
+    return false;
+}
+
+eError CArk::ConstructFromDirectory(const char* lpInputDirectory, const CArk& lReferenceHeader, std::vector<SSongConfig> laSongs)
+{
+    for (const char* lpAlways : {"/songs/credits", "/songs/tut0", "/songs/tut1", "/songs/tutc"}) {
+        SSongConfig lSong;
+        lSong.mPath = lpAlways;
+        laSongs.push_back(lSong);
+    }
+
+    std::string lRoot = lpInputDirectory;
+    if (!lRoot.empty() && lRoot.back() != '/')
+        lRoot += '/';
+    std::vector<std::string> laFilenames;
+    ListFiles(lRoot, "", laFilenames);
+    if (laFilenames.empty()) {
+        eError leError = eError_NoData;
+        SHOW_ERROR_AND_RETURN;
+    }
+    VERBOSE_OUT("Found " << laFilenames.size() << " files\n");
+
+    mHeader = modark::HeaderImage();
+    mHeader.mbPS4 = CSettings::mbPS4;
+    uint64_t luTotalFileSize = 0;
+    for (const std::string& lFilename : laFilenames) {
+        const modark::FileDef* lpReference = nullptr;
+        for (const modark::FileDef& lCandidate : lReferenceHeader.mHeader.maFiles) {
+            if (lCandidate.mName == lFilename) {
+                lpReference = &lCandidate;
+                break;
+            }
+        }
+        if (!lpReference && CSettings::mbIgnoreNewFiles)
+            continue;  // only files the reference header knows are repacked (-pack); -pack_add lifts this
+        if (!CSettings::mbPackAllFiles && !ShouldPackFile(laSongs, lFilename.c_str()))
+            continue;
+        const long liSize = FileSize(lRoot + lFilename);
+        if (liSize < 0) {
+            std::cout << "Unable to open file: " << lFilename.c_str() << "\n";
+            continue;
+        }
+        modark::FileDef lFile = lpReference ? *lpReference : modark::FileDef();
+        lFile.mName = lFilename;
+        lFile.miSize = (int)liSize;
+        luTotalFileSize += (uint64_t)liSize;
+        mHeader.maFiles.push_back(lFile);
+    }
+    if (mHeader.maFiles.empty()) {
+        eError leError = eError_NoData;
+        SHOW_ERROR_AND_RETURN;
+    }
+
+    // part plan: the reference header's part list, each part allowed an equal share of what is left
+    mHeader.maParts = lReferenceHeader.mHeader.maParts;
+    uint64_t luSizeRemaining = luTotalFileSize;
+    const size_t liNumArks = mHeader.maParts.size();
+    for (size_t ii = 0; ii < liNumArks; ++ii) {
+        mHeader.maParts[ii].muSize = (unsigned int)(luSizeRemaining / (liNumArks - ii));
+        luSizeRemaining -= mHeader.maParts[ii].muSize;
+    }
+    mbLoaded = true;
+    return eError_NoError;
+}
+
+eError CArk::BuildArk(const char* lpInputDirectory, std::vector<SSongConfig> laSongs)
+{
+    (void)laSongs;  // the reference appends its four defaults and never reads them here (CArk.cpp:762-765)
+    VERBOSE_OUT("Building ark\n");
+    if (mHeader.maParts.empty())
+        return eError_NoData;
+
+    uint64_t luTotalArkSize = 0;
+    for (const modark::FileDef& lFile : mHeader.maFiles)
+        luTotalArkSize += (uint64_t)lFile.miSize;
+    ReleaseArkData();
+    mpArkData = (unsigned char*)mod_host_alloc(luTotalArkSize + 1);
+    if (!mpArkData) {
+        std::cout << "Failed to allocate pinned memory for the archive: " << mod_last_error() << "\n";
+        return eError_NoData;
+    }
+    muArkDataSize = luTotalArkSize;
+
+    std::string lRoot = lpInputDirectory;
+    size_t liArkIndex = 0;
+    int64_t li64Allowed = mHeader.maParts[0].muSize;
+    uint64_t luPtr = 0, luPartStart = 0;
+    std::vector<mod_desc> laDescs;
+    bool lbAnyKey = false;
+    for (size_t ii = 0; ii < mHeader.maFiles.size(); ++ii) {
+        modark::FileDef& lFile = mHeader.maFiles[ii];
+        if (lFile.miSize == 0) {
+            lFile.mi64Offset = 0;
+            continue;
+        }
+        const std::string lFilename = lRoot + lFile.mName;
+        FILE* lpInputFile = std::fopen(lFilename.c_str(), "rb");
+        if (!lpInputFile) {
+            eError leError = eError_FailedToOpenFile;
+            SHOW_ERROR_AND_RETURN;
+        }
+        // scatter: the file lands at the running, byte-packed offset
+        lFile.mi64Offset = (int64_t)luPtr;
+        const size_t liRead = std::fread(mpArkData + luPtr, 1, (size_t)lFile.miSize, lpInputFile);
+        std::fclose(lpInputFile);
+        if (liRead != (size_t)lFile.miSize)
+            std::memset(mpArkData + luPtr + liRead, 0, (size_t)lFile.miSize - liRead);
+        const int liKey = EntryKey(ii);
+        lbAnyKey = lbAnyKey || (liKey % 0x7FFFFFFF) != 0;
+        laDescs.push_back(mod_desc{luPtr, luPtr, (uint32_t)lFile.miSize, liKey});
+        luPtr += (uint64_t)lFile.miSize;
+
+        // a part closes once it EXCEEDS its allowance; the overshoot shortens the next allowance
+        if ((int64_t)(luPtr - luPartStart) > li64Allowed) {
+            const unsigned int liArkSize = (unsigned int)(luPtr - luPartStart);
+            mHeader.maParts[liArkIndex].muSize = liArkSize;
+            if (liArkIndex + 1 >= mHeader.maParts.size()) {
+                // the reference would index past mpArks here (CArk.cpp:817-818); grow a part instead
+                modark::PartDef lExtra = mHeader.maParts[liArkIndex];
+                lExtra.mPath += ".extra";
+                lExtra.muSize = 0;
+                mHeader.maParts.push_back(lExtra);
+            }
+            ++liArkIndex;
+            li64Allowed += (int64_t)mHeader.maParts[liArkIndex].muSize - (int64_t)liArkSize;
+            luPartStart = luPtr;
+        }
+    }
+    mHeader.maParts[liArkIndex].muSize = (unsigned int)(luPtr - luPartStart);
+
+    // entries that carry a key are ciphered where they lie, all in one batched launch
+    if (lbAnyKey && !laDescs.empty()) {
+        if (mod_cycle_batch(laDescs.data(), laDescs.size(), mpArkData, muArkDataSize, mpArkData, muArkDataSize) != MOD_OK) {
+            std::cout << "GPU build failed: " << mod_last_error() << "\n";
+            return eError_InvalidData;
+        }
+    }
+    VERBOSE_OUT("Ark built\n");
+    return eError_NoError;
+}
+
+eError CArk::SaveArk(const char* lpOutputDirectory, const char* lpHeaderFilename) const
+{
+    // header: serialise on the host, encipher everything after the magic on the GPU, write
+    std::vector<unsigned char> lImage = modark::SerialiseHeader(mHeader);
+    CEncryptionCycler lEncrypt;
+    lEncrypt.Cycle(lImage.data() + sizeof(uint32_t), (unsigned int)(lImage.size() - sizeof(uint32_t)),
+                   (int)(mHeader.mbPS4 ? CSettings::kuEncryptedPS4Key : CSettings::kuEncryptedPS3Key));
+
+    const std::string lHeaderPath = std::string(lpOutputDirectory) + lpHeaderFilename;
+    if (KeepExistingOutput(lHeaderPath)) {
+        VERBOSE_OUT("Output file already exists, skipping: " << lHeaderPath.c_str() << "\n");
+    } else {
+        MakeParentDirectories(lHeaderPath);
+        VERBOSE_OUT("Writing " << lHeaderPath.c_str() << "\n");
+        FILE* lpOutputFile = std::fopen(lHeaderPath.c_str(), "wb");
+        if (lpOutputFile) {
+            const size_t liWritten = std::fwrite(lImage.data(), 1, lImage.size(), lpOutputFile);
+            std::fclose(lpOutputFile);
+            if (liWritten != lImage.size()) {
+                eError leError = eError_FailedToWriteData;
+                SHOW_ERROR_AND_RETURN;
+            }
+        } else {
+            std::cout << "Failed to open file for writing: " << lHeaderPath.c_str() << "\n";
+        }
+    }
+
+    // parts: consecutive slices of the image
+    const unsigned char* lpArkPtr = mpArkData;
+    for (const modark::PartDef& lPart : mHeader.maParts) {
+        const std::string lFilename = std::string(lpOutputDirectory) + lPart.mPath;
+        if (KeepExistingOutput(lFilename)) {
+            std::cout << "Output file already exists: " << lFilename.c_str() << "\n";
+            continue;  // like the reference, the cursor does not advance past a skipped part (CArk.cpp:863-868)
+        }
+        std::cout << "Writing " << lFilename.c_str() << "\n";
+        MakeParentDirectories(lFilename);
+        FILE* lpOutputFile = std::fopen(lFilename.c_str(), "wb");
+        if (!lpOutputFile) {
+            std::cout << "Failed to open file for writing: " << lFilename.c_str() << "\n";
+            continue;
+        }
+        const size_t liWritten = (lPart.muSize && lpArkPtr) ? std::fwrite(lpArkPtr, 1, lPart.muSize, lpOutputFile) : 0;
+        std::fclose(lpOutputFile);
+        if (liWritten != lPart.muSize) {
+            eError leError = eError_FailedToWriteData;
+            SHOW_ERROR_AND_RETURN;
+        }
+        lpArkPtr += lPart.muSize;
+    }
+    return eError_NoError;
+}

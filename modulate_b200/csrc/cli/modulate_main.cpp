@@ -1,0 +1,239 @@
+// modulate_main.cpp -- portable command line over the facade: the reference's archive commands
+// (-ps3 -verbose -force -packall -unpack -pack -pack_add -decode; Modulate.cpp:45-70, :291-317,
+// :380-502, :895-972) with the same left-to-right command deque and exit convention.  The song /
+// DTA commands of the reference are host-side tooling outside the hot path and are not provided.
+//
+// Extensions: -bodykey K (cipher every entry body with key K, stream restarting per entry -- the
+// synthetic per-entry-key configurations), -device N (bind GPU N).
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <iostream>
+#include <string>
+#include <strings.h>
+#include <vector>
+
+#include "../../../include/modulate_b200.h"
+#include "../CArk.h"
+#include "../CEncryptionCycler.h"
+#include "../Error.h"
+#include "../Settings.h"
+
+namespace {
+
+int giBodyKey = 0;
+
+std::string HeaderName() { return std::string("main_") + CSettings::msPlatform + ".hdr"; }
+
+void WithSlash(std::string& lPath)
+{
+    if (lPath.empty() || (lPath.back() != '/' && lPath.back() != '\\'))
+        lPath += "/";
+}
+
+eError PS3(std::deque<std::string>&)
+{
+    CSettings::mbPS4 = false;
+    CSettings::msPlatform = "ps3";
+    return eError_NoError;
+}
+
+eError EnableVerbose(std::deque<std::string>&)
+{
+    CSettings::mbVerbose = true;
+    return eError_NoError;
+}
+
+eError EnableForceWrite(std::deque<std::string>&)
+{
+    CSettings::mbOverwriteOutputFiles = true;
+    return eError_NoError;
+}
+
+eError EnablePackAll(std::deque<std::string>&)
+{
+    CSettings::mbPackAllFiles = true;
+    return eError_NoError;
+}
+
+eError BodyKey(std::deque<std::string>& laParams)
+{
+    if (laParams.empty())
+        return eError_InvalidParameter;
+    giBodyKey = (int)std::strtoll(laParams.front().c_str(), nullptr, 0);
+    laParams.pop_front();
+    return eError_NoError;
+}
+
+eError Device(std::deque<std::string>& laParams)
+{
+    if (laParams.empty())
+        return eError_InvalidParameter;
+    const int liDevice = std::atoi(laParams.front().c_str());
+    laParams.pop_front();
+    if (mod_init(liDevice) != MOD_OK) {
+        std::cout << mod_last_error() << "\n";
+        return eError_InvalidParameter;
+    }
+    return eError_NoError;
+}
+
+eError Unpack(std::deque<std::string>& laParams)
+{
+    std::cout << "Unpacking " << HeaderName() << " to ";
+    if (laParams.empty())
+        return eError_InvalidParameter;
+    std::string lOutputDirectory = laParams.front();
+    laParams.pop_front();
+    std::cout << lOutputDirectory << "\n";
+    WithSlash(lOutputDirectory);
+
+    CArk lArkHeader;
+    lArkHeader.SetUniformEntryKey(giBodyKey);
+    eError leError = lArkHeader.Load(HeaderName().c_str());
+    SHOW_ERROR_AND_RETURN;
+    leError = lArkHeader.ExtractFiles(0, lArkHeader.GetNumFiles(), lOutputDirectory.c_str());
+    SHOW_ERROR_AND_RETURN;
+    return eError_NoError;
+}
+
+eError PackImpl(std::deque<std::string>& laParams)
+{
+    std::cout << "Packing " << HeaderName() << " from ";
+    if (laParams.empty())
+        return eError_InvalidParameter;
+    std::string lInputPath = laParams.front();
+    laParams.pop_front();
+    std::cout << lInputPath << " to ";
+    if (laParams.empty())
+        return eError_InvalidParameter;
+    std::string lOutputPath = laParams.front();
+    laParams.pop_front();
+    std::cout << lOutputPath << "\n";
+    WithSlash(lInputPath);
+    WithSlash(lOutputPath);
+
+    // The reference derives the song list from the DTA configs unless -packall is given
+    // (Modulate.cpp:410-432); that DTA tooling is out of scope here, so the list is empty and the
+    // /songs/ filter keeps only the four built-in songs unless -packall.
+    std::vector<SSongConfig> lSongs;
+
+    CArk lReferenceArkHeader;
+    eError leError = lReferenceArkHeader.Load(HeaderName().c_str());
+    SHOW_ERROR_AND_RETURN;
+
+    CArk lArkHeader;
+    lArkHeader.SetUniformEntryKey(giBodyKey);
+    leError = lArkHeader.ConstructFromDirectory(lInputPath.c_str(), lReferenceArkHeader, lSongs);
+    SHOW_ERROR_AND_RETURN;
+    leError = lArkHeader.BuildArk(lInputPath.c_str(), lSongs);
+    SHOW_ERROR_AND_RETURN;
+    leError = lArkHeader.SaveArk(lOutputPath.c_str(), HeaderName().c_str());
+    SHOW_ERROR_AND_RETURN;
+    return eError_NoError;
+}
+
+eError Pack(std::deque<std::string>& laParams) { return PackImpl(laParams); }
+
+eError AddPack(std::deque<std::string>& laParams)
+{
+    CSettings::mbIgnoreNewFiles = false;  // reference Modulate.cpp:580-586
+    return PackImpl(laParams);
+}
+
+eError Decode(std::deque<std::string>&)
+{
+    const std::string lHeaderFilename = HeaderName();
+    FILE* lpHeaderFile = std::fopen(lHeaderFilename.c_str(), "rb");
+    if (!lpHeaderFile)
+        return eError_FailedToOpenFile;
+    std::fseek(lpHeaderFile, 0, SEEK_END);
+    const long liHeaderSize = std::ftell(lpHeaderFile);
+    std::fseek(lpHeaderFile, 0, SEEK_SET);
+    std::vector<unsigned char> lData((size_t)std::max(0l, liHeaderSize));
+    const size_t liRead = lData.empty() ? 0 : std::fread(lData.data(), 1, lData.size(), lpHeaderFile);
+    std::fclose(lpHeaderFile);
+    if (liRead != lData.size() || lData.size() < 4)
+        return eError_UnknownVersionNumber;
+
+    unsigned int luVersion = 0;
+    std::memcpy(&luVersion, lData.data(), 4);
+    if (luVersion != CSettings::kuEncryptedVersionPS3 && luVersion != CSettings::kuEncryptedVersionPS4)
+        return eError_UnknownVersionNumber;
+    const unsigned int kuInitialKey =
+        (luVersion == CSettings::kuEncryptedVersionPS3) ? CSettings::kuEncryptedPS3Key : CSettings::kuEncryptedPS4Key;
+    CEncryptionCycler lDecrypt;
+    lDecrypt.Cycle(lData.data() + 4, (unsigned int)(lData.size() - 4), (int)kuInitialKey);
+
+    const std::string lOut = lHeaderFilename + ".dec";
+    FILE* lpOut = std::fopen(lOut.c_str(), "wb");
+    if (!lpOut)
+        return eError_FailedToCreateFile;
+    const size_t liWritten = std::fwrite(lData.data(), 1, lData.size(), lpOut);
+    std::fclose(lpOut);
+    return liWritten == lData.size() ? eError_NoError : eError_FailedToWriteData;
+}
+
+void PrintUsage()
+{
+    std::cout << "Usage: modulate <options> <command>\n\n"
+              << "Options:\n"
+              << "  -verbose        Show additional information during operation\n"
+              << "  -ps3            Switch to PS3 mode (default PS4)\n"
+              << "  -force          Overwrite existing output files\n"
+              << "  -packall        Pack every file found, bypassing the /songs/ filter\n"
+              << "  -bodykey <k>    Cipher entry bodies with key k (extension; default 0 = plain, like the game)\n"
+              << "  -device <n>     Run on GPU n\n\n"
+              << "Commands:\n"
+              << "  -unpack <out_dir>           Unpack main_<platform>.hdr (+ .ark parts) from the current directory\n"
+              << "  -pack <in_dir> <out_dir>    Repack the files the reference header knows\n"
+              << "  -pack_add <in_dir> <out_dir> Repack, also adding new files\n"
+              << "  -decode                     Write the deciphered header to main_<platform>.hdr.dec\n";
+}
+
+}  // namespace
+
+int main(int argc, char* argv[])
+{
+    struct sCommandPair {
+        const char* mpCommandName;
+        std::function<eError(std::deque<std::string>&)> mFunction;
+    };
+    const sCommandPair kaCommands[] = {
+        {"-ps3", PS3},       {"-verbose", EnableVerbose}, {"-force", EnableForceWrite}, {"-packall", EnablePackAll},
+        {"-bodykey", BodyKey}, {"-device", Device},       {"-unpack", Unpack},          {"-pack", Pack},
+        {"-pack_add", AddPack}, {"-decode", Decode},
+    };
+
+    std::deque<std::string> laParams;
+    for (int ii = 1; ii < argc; ++ii)
+        laParams.push_back(argv[ii]);
+    if (laParams.empty()) {
+        PrintUsage();
+        return 0;
+    }
+    while (!laParams.empty()) {
+        bool lbMatched = false;
+        for (const sCommandPair& lCommand : kaCommands) {
+            if (strcasecmp(laParams.front().c_str(), lCommand.mpCommandName) != 0)
+                continue;
+            lbMatched = true;
+            laParams.pop_front();
+            const eError leError = lCommand.mFunction(laParams);
+            if (leError != eError_NoError) {
+                ShowError(leError);
+                return -1;
+            }
+            std::cout << "\n";
+            break;
+        }
+        if (!lbMatched) {
+            std::cout << "Unkown parameter: " << laParams.front() << "\nAborting\n\n";
+            PrintUsage();
+            return -1;
+        }
+    }
+    std::cout << "Complete!\n";
+    return 0;
+}

@@ -1,0 +1,192 @@
+"""CPU: the host-side C++ (CArk facade, ArkHeader codec, CLI) driven end to end through a MOCK of
+the C ABI that answers with the oracle (tests/cpp/mock_abi.cpp).  Same flows run on the GPU with
+the real library in tests/test_gpu_facade.py."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import synth
+from oracle import ark_oracle as ao
+import arkfixture
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "modulate_b200", "csrc")
+BUILD = os.path.join(ROOT, "tests", "_build")
+MOCK = os.path.join(BUILD, "modulate_mock")
+
+
+@pytest.fixture(scope="session")
+def cli():
+    """modulate CLI linked against the oracle-backed mock ABI (g++ only, no CUDA)."""
+    oracle.build()
+    os.makedirs(BUILD, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cpp"))) + [os.path.join(CSRC, "cli", "modulate_main.cpp"),
+                                                              os.path.join(ROOT, "tests", "cpp", "mock_abi.cpp")]
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.h")) + [os.path.join(ROOT, "include", "modulate_b200.h")]
+    if not os.path.exists(MOCK) or any(os.path.getmtime(d) > os.path.getmtime(MOCK) for d in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", MOCK,
+                               *srcs, "-L", os.path.join(ROOT, "oracle"), "-loracle",
+                               f"-Wl,-rpath,{os.path.join(ROOT, 'oracle')}"])
+    return MOCK
+
+
+def run(cli, cwd, *args, expect=0):
+    out = subprocess.run([cli, *args], cwd=cwd, capture_output=True, text=True, timeout=300)
+    assert out.returncode == (expect if expect == 0 else 255), out.stdout + out.stderr
+    return out.stdout
+
+
+def check_unpacked(out_dir, hdr, payloads):
+    for e, p in zip(hdr.entries, payloads):
+        got = open(os.path.join(out_dir, e.name), "rb").read()
+        assert got == p, e.name
+
+
+@pytest.mark.parametrize("ps4", [True, False])
+def test_unpack_matches_oracle_gather(cli, tmp_path, ps4):
+    hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), ps4=ps4, n_files=80, n_parts=3, seed=3)
+    # the oracle's own view of the archive: parts -> flat image -> gather by (offset, size)
+    blobs = [open(tmp_path / p, "rb").read() for p, _ in hdr.parts]
+    assert ao.extract(hdr.entries, ao.load_ark_data(blobs)) == payloads
+    args = ([] if ps4 else ["-ps3"]) + ["-unpack", "out"]
+    stdout = run(cli, tmp_path, *args)
+    assert "Complete!" in stdout
+    check_unpacked(tmp_path / "out", hdr, payloads)
+
+
+def test_unpack_with_body_key(cli, tmp_path):
+    key = 0x12345678
+    hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), n_files=40, n_parts=2, seed=5, body_key=key)
+    run(cli, tmp_path, "-bodykey", str(key), "-unpack", "out")
+    check_unpacked(tmp_path / "out", hdr, payloads)
+
+
+def test_decode_matches_oracle(cli, tmp_path):
+    for ps4 in (True, False):
+        d = tmp_path / ("p4" if ps4 else "p3")
+        _, _, plain = arkfixture.write_archive(str(d), ps4=ps4, n_files=30, seed=7)
+        run(cli, d, *([] if ps4 else ["-ps3"]), "-decode")
+        plat = "ps4" if ps4 else "ps3"
+        assert open(d / f"main_{plat}.hdr.dec", "rb").read() == plain
+
+
+def test_load_rejects_bad_headers(cli, tmp_path):
+    hdr, _, plain = arkfixture.write_archive(str(tmp_path), n_files=10, seed=9)
+    path = tmp_path / "main_ps4.hdr"
+    good = path.read_bytes()
+    path.write_bytes(b"\x01\x02\x03\x04" + good[4:])                # unknown magic
+    assert "Unknown version number" in run(cli, tmp_path, "-unpack", "o", expect=1)
+    bad = bytearray(plain)
+    bad[4 + 24:4 + 28] = (101).to_bytes(4, "little")                # numArks > 100
+    enc = bytes(bad[:4]) + oracle.cycle(np.frombuffer(bytes(bad[4:]), np.uint8), ao.KEY_PS4).tobytes()
+    path.write_bytes(enc)
+    assert "Value of out bounds" in run(cli, tmp_path, "-unpack", "o", expect=1)
+    path.write_bytes(good[:len(good) // 2])                          # truncated: bounds-checked, not UB
+    assert "Bad data" in run(cli, tmp_path, "-unpack", "o", expect=1)
+    os.remove(path)
+    assert "Failed to open file" in run(cli, tmp_path, "-unpack", "o", expect=1)
+
+
+@pytest.mark.parametrize("ps4", [True, False])
+def test_pack_roundtrip_offsets_parts_and_header_bytes(cli, tmp_path, ps4):
+    """unpack -> pack_add -packall -> the rebuilt set: offsets and part sizes follow the oracle's
+    BuildArk restatement, the image is the byte-packed payloads, and the header bytes equal the
+    oracle's serialiser (PS3: its own bucket order; PS4: the order the C++ chose)."""
+    plat = "ps4" if ps4 else "ps3"
+    pre = [] if ps4 else ["-ps3"]
+    hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), ps4=ps4, n_files=70, n_parts=3, seed=11)
+    run(cli, tmp_path, *pre, "-unpack", "unpacked")
+    run(cli, tmp_path, *pre, "-packall", "-pack_add", "unpacked", "repacked")
+    new, plain = arkfixture.read_header(str(tmp_path / "repacked" / f"main_{plat}.hdr"))
+    by_name = {e.name: p for e, p in zip(hdr.entries, payloads)}
+    assert sorted(e.name for e in new.entries) == sorted(by_name)
+    # the C++ packs files in its directory-walk order; recover it from the offsets
+    packed = sorted([e for e in new.entries if e.size], key=lambda e: e.offset)
+    walk = [e.name for e in packed]
+    sizes_in_walk = [len(by_name[n]) for n in walk]
+    total = sum(sizes_in_walk)
+    want_off, want_parts = ao.build_ark(sizes_in_walk, ao.plan_part_sizes(total, len(hdr.parts)))
+    assert [e.offset for e in packed] == want_off
+    assert [s for _, s in new.parts] == want_parts
+    assert all(e.offset == 0 for e in new.entries if e.size == 0)
+    image = b"".join(open(tmp_path / "repacked" / p, "rb").read() for p, _ in new.parts)
+    assert image == b"".join(by_name[n] for n in walk)
+    # header bytes: feed the oracle serialiser the same table (in C++ table order = walk order incl. empties)
+    table_order_names = [e.name for e in new.entries]
+    ref_entries = {e.name: e for e in new.entries}
+    # reconstruct the in-memory table the C++ serialised: directory-walk order (files first, then dirs)
+    table = reconstruct_walk(sorted(by_name), by_name)
+    tbl = [ao.Entry(name=n, offset=ref_entries[n].offset, size=ref_entries[n].size) for n in table]
+    model = ao.Header(ps4=ps4, parts=new.parts, entries=tbl)
+    order = None if not ps4 else [table.index(n) for n in table_order_names]
+    assert ao.serialise_header(model, order=order) == plain
+    # and it round-trips through unpack again
+    os.makedirs(tmp_path / "again", exist_ok=True)
+    for p, _ in new.parts:
+        os.replace(tmp_path / "repacked" / p, tmp_path / "again" / p)
+    os.replace(tmp_path / "repacked" / f"main_{plat}.hdr", tmp_path / "again" / f"main_{plat}.hdr")
+    run(cli, tmp_path / "again", *pre, "-unpack", "out")
+    check_unpacked(tmp_path / "again" / "out", hdr, payloads)
+
+
+def reconstruct_walk(names, by_name):
+    """Directory walk order of the facade: per directory, files (case-insensitive) then sub-directories."""
+    tree = {}
+    for n in names:
+        node = tree
+        parts = n.split("/")
+        for p in parts[:-1]:
+            node = node.setdefault(("d", p), {})
+        node[("f", parts[-1])] = n
+    out = []
+
+    def walk(node):
+        files = sorted([k for k in node if k[0] == "f"], key=lambda k: k[1].lower())
+        dirs = sorted([k for k in node if k[0] == "d"], key=lambda k: k[1].lower())
+        for k in files:
+            out.append(node[k])
+        for k in dirs:
+            walk(node[k])
+    walk(tree)
+    return out
+
+
+def test_pack_filters_unknown_files_and_songs(cli, tmp_path):
+    hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), n_files=50, n_parts=2, seed=13)
+    run(cli, tmp_path, "-unpack", "unpacked")
+    (tmp_path / "unpacked" / "ps4" / "brand_new.bin").write_bytes(b"new file")
+    run(cli, tmp_path, "-pack", "unpacked", "r1")                       # default: ignore new + /songs/ filter
+    new, _ = arkfixture.read_header(str(tmp_path / "r1" / "main_ps4.hdr"))
+    names = {e.name for e in new.entries}
+    assert "ps4/brand_new.bin" not in names
+    assert not any("/songs/custom1/" in n for n in names)
+    assert any("/songs/credits/" in n for n in names) or not any("/songs/credits/" in e.name for e in hdr.entries)
+    run(cli, tmp_path, "-packall", "-pack_add", "unpacked", "r2")      # everything
+    new2, _ = arkfixture.read_header(str(tmp_path / "r2" / "main_ps4.hdr"))
+    assert {e.name for e in new2.entries} == {e.name for e in hdr.entries} | {"ps4/brand_new.bin"}
+
+
+def test_header_codec_roundtrip_python_side():
+    """Load's reader parses what lSaveHeader's writer emits (oracle restatement of both)."""
+    for ps4 in (True, False):
+        names = arkfixture.make_names(200, seed=21)
+        entries = [ao.Entry(name=n, offset=i * 100, size=(i % 7) * 10) for i, n in enumerate(names)]
+        hdr = ao.Header(ps4=ps4, parts=[("a.ark", 1000), ("b.ark", 2000)], entries=entries)
+        back = ao.parse_header(ao.serialise_header(hdr))
+        assert back.parts == hdr.parts and back.ps4 == ps4
+        assert sorted((e.name, e.offset, e.size) for e in back.entries) == sorted((e.name, e.offset, e.size) for e in entries)
+        # every bucket chain reaches every entry of the bucket exactly once
+        n = len(back.entries)
+        reached = set()
+        for b in range(n):
+            idx = back.entries[b].flags2 if b < n else -1
+            while idx != -1:
+                assert idx not in reached
+                reached.add(idx)
+                assert ao.file_hash(back.entries[idx].name, n) == b
+                idx = back.entries[idx].flags1
+        assert reached == set(range(n))

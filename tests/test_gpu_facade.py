@@ -1,0 +1,81 @@
+"""GPU: the C++ facade (CEncryptionCycler / CArk) and the CLI linked against the REAL CUDA library:
+the same archive flows as tests/test_facade_host.py, checked against the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import synth
+from oracle import ark_oracle as ao
+import arkfixture
+from test_facade_host import check_unpacked, reconstruct_walk
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "modulate_b200", "bin", "modulate")
+
+
+def run(cwd, *args, expect=0):
+    assert os.path.exists(CLI), "modulate CLI not built (python -m modulate_b200.build)"
+    out = subprocess.run([CLI, *args], cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == (0 if expect == 0 else 255), out.stdout + out.stderr
+    return out.stdout
+
+
+def test_cli_links_the_cuda_library():
+    out = subprocess.run(["ldd", CLI], capture_output=True, text=True).stdout
+    assert "libmodulate_b200.so" in out and "not found" not in out.split("libmodulate_b200.so")[1].split("\n")[0]
+
+
+@pytest.mark.parametrize("ps4", [True, False])
+def test_unpack_on_gpu(tmp_path, ps4):
+    hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), ps4=ps4, n_files=300, n_parts=4, seed=31)
+    run(tmp_path, *([] if ps4 else ["-ps3"]), "-unpack", "out")
+    check_unpacked(tmp_path / "out", hdr, payloads)
+
+
+def test_unpack_ciphered_bodies_on_gpu(tmp_path):
+    key = -559038737  # 0xDEADBEEF as int
+    sizes = [int(x) for x in np.random.default_rng(2).integers(0, 300000, size=120)]
+    hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), n_files=120, n_parts=3, seed=33, body_key=key, sizes=sizes)
+    run(tmp_path, "-bodykey", str(key), "-unpack", "out")
+    check_unpacked(tmp_path / "out", hdr, payloads)
+
+
+def test_decode_on_gpu(tmp_path):
+    _, _, plain = arkfixture.write_archive(str(tmp_path), n_files=500, seed=35)
+    run(tmp_path, "-decode")
+    assert open(tmp_path / "main_ps4.hdr.dec", "rb").read() == plain
+
+
+@pytest.mark.parametrize("ps4", [True, False])
+def test_repack_on_gpu_end_to_end(tmp_path, ps4):
+    """BASELINE config 5 in miniature: extract, patch one DTA-like entry on the host, rebuild offsets
+    and parts, re-encipher bodies + header, write; then read it all back."""
+    plat = "ps4" if ps4 else "ps3"
+    pre = [] if ps4 else ["-ps3"]
+    key = 0x0BADF00D
+    hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), ps4=ps4, n_files=150, n_parts=3, seed=37, body_key=key)
+    run(tmp_path, *pre, "-bodykey", str(key), "-unpack", "unpacked")
+    victim = next(e for e in hdr.entries if e.size > 100)
+    patched = b"(patched dta)" * 50
+    open(tmp_path / "unpacked" / victim.name, "wb").write(patched)
+    run(tmp_path, *pre, "-bodykey", str(key), "-packall", "-pack_add", "unpacked", "repacked")
+    new, plain = arkfixture.read_header(str(tmp_path / "repacked" / f"main_{plat}.hdr"))
+    by_name = {e.name: p for e, p in zip(hdr.entries, payloads)}
+    by_name[victim.name] = patched
+    packed = sorted([e for e in new.entries if e.size], key=lambda e: e.offset)
+    sizes_in_walk = [len(by_name[e.name]) for e in packed]
+    want_off, want_parts = ao.build_ark(sizes_in_walk, ao.plan_part_sizes(sum(sizes_in_walk), len(hdr.parts)))
+    assert [e.offset for e in packed] == want_off and [s for _, s in new.parts] == want_parts
+    image = np.frombuffer(b"".join(open(tmp_path / "repacked" / p, "rb").read() for p, _ in new.parts), np.uint8)
+    for e in packed:  # bodies are ciphered per entry with the body key
+        assert oracle.cycle(image[e.offset:e.offset + e.size], key).tobytes() == by_name[e.name], e.name
+    table = reconstruct_walk(sorted(by_name), by_name)
+    ref = {e.name: e for e in new.entries}
+    model = ao.Header(ps4=ps4, parts=new.parts, entries=[ao.Entry(name=n, offset=ref[n].offset, size=ref[n].size) for n in table])
+    order = None if not ps4 else [table.index(e.name) for e in new.entries]
+    assert ao.serialise_header(model, order=order) == plain
