@@ -115,9 +115,7 @@ int mod_plan_run(const mod_plan* plan, const void* d_src, void* d_dst, void* str
 
 /* Convenience: plan + run + destroy, synchronous.  `src` / `dst` are both host pointers (staged
  * through HBM in groups of entries, upload / kernel / download overlapped) or both device pointers.
- * Host form: bytes of dst not covered by any descriptor keep their value, except that a gap of
- * fewer than 16 bytes between two destination entries is treated as alignment padding and comes
- * back zero-filled.  (The device form writes covered bytes only.) */
+ * In both forms bytes of dst that no descriptor covers keep their value. */
 int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t src_bytes,
                     void* dst, uint64_t dst_bytes);
 

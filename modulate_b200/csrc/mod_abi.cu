@@ -604,30 +604,79 @@ int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t
         groups.assign(1, all);
     }
 
-    // Destination runs (maximal covered intervals) per group.  A batch whose destination is full of
-    // holes (more than 64 runs in a group) is handled exactly but without pipelining: the whole
-    // destination makes a round trip through HBM so that the holes keep their host bytes.
-    auto merged_runs = [&](const Group& g, std::vector<std::pair<uint64_t, uint64_t>>& runs) {
+    // Destination runs (maximal intervals downloaded with one copy) per group.  Two entries that are
+    // neighbours in the GLOBAL destination order and less than 16 bytes apart (alignment padding) are
+    // bridged into one run; the host bytes of such a gap are saved first and put back after the
+    // download, so every byte not covered by a descriptor keeps its value.  A batch whose destination
+    // is full of larger holes (more than 64 runs in a group) is handled exactly but without
+    // pipelining: the whole destination makes a round trip through HBM.
+    std::vector<uint32_t> rank(n, 0);      // position of each non-empty entry in global dst order
+    std::vector<uint8_t> bridge_after;     // by rank: the gap to the next entry may be bridged
+    {
+        std::vector<uint32_t> order;
+        order.reserve(n);
+        bool monotone = true;
+        uint64_t last = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            if (!descs[i].len)
+                continue;
+            if (descs[i].dst_off < last)
+                monotone = false;
+            last = descs[i].dst_off;
+            order.push_back((uint32_t)i);
+        }
+        if (!monotone)
+            std::sort(order.begin(), order.end(),
+                      [&](uint32_t a, uint32_t b) { return descs[a].dst_off < descs[b].dst_off; });
+        bridge_after.assign(order.size(), 0);
+        for (size_t r = 0; r < order.size(); ++r) {
+            rank[order[r]] = (uint32_t)r;
+            if (r + 1 < order.size()) {
+                const uint64_t end = descs[order[r]].dst_off + descs[order[r]].len;
+                const uint64_t nxt = descs[order[r + 1]].dst_off;
+                bridge_after[r] = (nxt >= end && nxt - end < 16) ? 1 : 0;
+            }
+        }
+    }
+    struct Gap {
+        uint64_t off;
+        uint32_t len;
+        uint8_t bytes[15];
+    };
+    std::vector<Gap> gaps;
+    std::vector<uint32_t> members;
+    auto merged_runs = [&](const Group& g, std::vector<std::pair<uint64_t, uint64_t>>& runs, bool save_gaps) {
         runs.clear();
+        members.clear();
         for (uint64_t i = g.e0; i < g.e1; ++i)
             if (descs[i].len)
-                runs.emplace_back(descs[i].dst_off, descs[i].dst_off + descs[i].len);
-        std::sort(runs.begin(), runs.end());
-        size_t m = 0;
-        for (size_t i = 0; i < runs.size(); ++i) {
-            // gaps of fewer than 16 bytes are alignment padding between entries: they are bridged
-            // and come back zero-filled (documented in include/modulate_b200.h)
-            if (m && runs[i].first < runs[m - 1].second + 16)
-                runs[m - 1].second = std::max(runs[m - 1].second, runs[i].second);
-            else
-                runs[m++] = runs[i];
+                members.push_back((uint32_t)i);
+        std::sort(members.begin(), members.end(), [&](uint32_t a, uint32_t b) { return rank[a] < rank[b]; });
+        uint32_t prev_rank = 0;
+        for (uint32_t idx : members) {
+            const uint64_t b0 = descs[idx].dst_off, b1 = b0 + descs[idx].len;
+            const bool adjacent = !runs.empty() && rank[idx] == prev_rank + 1;
+            if (adjacent && b0 <= runs.back().second) {
+                runs.back().second = std::max(runs.back().second, b1);
+            } else if (adjacent && bridge_after[prev_rank] && b0 - runs.back().second < 16) {
+                if (save_gaps && b0 > runs.back().second) {
+                    Gap gap;
+                    gap.off = runs.back().second;
+                    gap.len = (uint32_t)(b0 - runs.back().second);
+                    std::memcpy(gap.bytes, (const uint8_t*)dst + gap.off, gap.len);
+                    gaps.push_back(gap);
+                }
+                runs.back().second = b1;
+            } else {
+                runs.emplace_back(b0, b1);
+            }
+            prev_rank = rank[idx];
         }
-        runs.resize(m);
     };
     std::vector<std::pair<uint64_t, uint64_t>> runs;
     bool holes = false;
     for (const Group& g : groups) {
-        merged_runs(g, runs);
+        merged_runs(g, runs, false);
         if (runs.size() > 64) {
             holes = true;
             break;
@@ -648,16 +697,10 @@ int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t
                             cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess && holes)
             e = cudaMemcpyAsync(g_ctx.ws_dst, dst, dst_bytes, cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess && !holes) {  // zero the runs so that bridged padding is deterministic
-            merged_runs(g, runs);
-            for (const auto& r : runs) {
-                e = cudaMemsetAsync((uint8_t*)g_ctx.ws_dst + r.first, 0, r.second - r.first, s);
-                if (e != cudaSuccess)
-                    break;
-            }
-        }
         if (e != cudaSuccess)
             break;
+        if (!holes)
+            merged_runs(g, runs, true);
         modk::BatchArgs args;
         args.src = (const uint8_t*)g_ctx.ws_src;
         args.dst = (uint8_t*)g_ctx.ws_dst;
@@ -687,6 +730,9 @@ int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t
         if (e == cudaSuccess)
             e = es;
     }
+    if (e == cudaSuccess)
+        for (const Gap& gap : gaps)  // put the padding bytes the bridged downloads ran over back
+            std::memcpy((uint8_t*)dst + gap.off, gap.bytes, gap.len);
     if (trace)
         fprintf(stderr, "[mod] cycle_batch: plan %.2f ms, enqueue %zu groups %.2f ms, drain %.2f ms\n", t_plan - t_begin,
                 groups.size(), t_enq - t_plan, now_ms() - t_enq);

@@ -373,12 +373,5 @@ def test_batch_host_buffers_pipelined(mb, layout, monkeypatch):
     src = synth.payload(3, int((src_off + sizes).max()))
     dst = np.full(int((dst_off + sizes).max()) + 9, 0x77, np.uint8)
     want = oracle.cycle_batch(descs, src, dst.copy())
-    if layout == "packed":
-        # documented host-form rule: gaps of < 16 bytes between entries are padding and come back zero
-        covered = np.zeros(dst.size, bool)
-        for d in descs:
-            covered[int(d["dst_off"]):int(d["dst_off"]) + int(d["len"])] = True
-        span_end = int((dst_off + sizes).max())
-        want[:span_end][~covered[:span_end]] = 0
     mb.cycle_batch(descs, src, dst)
     assert (dst == want).all()
