@@ -44,6 +44,15 @@ using modlcg::low8_canonical;
 #ifndef MODK_MIN_CTAS
 #define MODK_MIN_CTAS 4          // resident CTAs per SM requested through __launch_bounds__ (64 registers)
 #endif
+#ifndef MODK_SPECULATE
+#define MODK_SPECULATE 1         // pack low bytes from lazy states, redo the ~1/8000 chunks that needed a canonical subtract
+#endif
+#ifndef MODK_BULK
+#define MODK_BULK 0              // 1: stage the source through a per-warp shared-memory ring filled by bulk-async copies (TMA 1-D)
+#endif
+#ifndef MODK_STAGES
+#define MODK_STAGES 8            // ring depth per warp (rounds of 512 B in flight) when MODK_BULK
+#endif
 #ifndef MODK_LD_HINT
 #define MODK_LD_HINT 0           // 0: ld.global   1: .L1::no_allocate on the co-aligned path   2: .cs everywhere
 #endif
@@ -106,9 +115,10 @@ __device__ __forceinline__ uint32_t low8_canonical_fma(uint32_t s, uint32_t two)
 }
 
 // XOR the 16 bytes of `d` with the keystream that follows (negated) state `s`, the state just
-// before the chunk's first byte.  Per byte: IMAD.WIDE + LEA.HI (step), IMAD.HI (canonical low
-// byte); per word: three PRMTs pack four keystream bytes and one LOP3 applies them.
-__device__ __forceinline__ uint4 cycle_chunk(uint4 d, uint32_t s, const uint32_t two)
+// before the chunk's first byte -- exact for every state.  Per byte: IMAD.WIDE + LEA.HI (step) and
+// a canonical low byte (LEA.HI on the ALU pipe or IMAD.HI on the FMA pipe, per MODK_CANON_FMA_MASK);
+// per word: three PRMTs pack four keystream bytes and one LOP3 applies them.
+__device__ __forceinline__ uint4 cycle_chunk_exact(uint4 d, uint32_t s, const uint32_t two)
 {
     uint32_t w[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
@@ -127,6 +137,106 @@ __device__ __forceinline__ uint4 cycle_chunk(uint4 d, uint32_t s, const uint32_t
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
+
+// Out-of-line copy of the exact form for the rare chunks the speculative form below hands over.
+__device__ __noinline__ uint4 cycle_chunk_rare(uint4 d, uint32_t s, uint32_t two)
+{
+    return cycle_chunk_exact(d, s, two);
+}
+
+// Speculative form used in the hot loop.  A lazily reduced state t = hi + lo31 (hi <= 16807) is
+// already canonical unless bit 31 is set, which needs lo31 >= 2^31 - 16807: about 2^-17 per byte.
+// So the 16 low bytes are packed straight from the lazy states, the states are OR-ed together
+// (8 three-input LOP3 instead of 16 canonicalisations), and only if some state had bit 31 set is
+// the chunk redone by the exact routine (about one chunk in 8 000).
+__device__ __forceinline__ uint4 cycle_chunk(uint4 d, uint32_t s, const uint32_t two)
+{
+#if MODK_SPECULATE
+    const uint32_t s0 = s;
+    uint32_t w[4] = {d.x, d.y, d.z, d.w};
+    uint32_t any = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t b0 = step_lazy(s);
+        const uint32_t b1 = step_lazy(b0);
+        const uint32_t b2 = step_lazy(b1);
+        const uint32_t b3 = step_lazy(b2);
+        s = b3;
+        any |= b0 | b1;
+        any |= b2 | b3;
+        const uint32_t lo = __byte_perm(b0, b1, 0x0040);
+        const uint32_t hi = __byte_perm(b2, b3, 0x0040);
+        w[j] ^= __byte_perm(lo, hi, 0x5410);
+    }
+    if (__builtin_expect((int32_t)any < 0, 0))
+        return cycle_chunk_rare(d, s0, two);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+#else
+    return cycle_chunk_exact(d, s, two);
+#endif
+}
+
+// The 16 keystream bytes that follow state `s`, as four little-endian words (no data involved, so
+// the bulk-staged path computes them while its source bytes are still in flight).
+__device__ __forceinline__ uint4 keystream_chunk(uint32_t s, const uint32_t two)
+{
+    return cycle_chunk(make_uint4(0u, 0u, 0u, 0u), s, two);
+}
+
+#if MODK_BULK
+// ---- bulk-async staging: mbarrier + cp.async.bulk (SASS: UBLKCP / SYNCS) --------------------------------
+constexpr int kStages = MODK_STAGES;
+constexpr uint32_t kStageBytes = 512u + 16u;  // 32 granules + the one the last lane straddles into
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MODK_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MODK_DONE;\n"
+        "bra MODK_WAIT;\n"
+        "MODK_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); completion
+// is signalled on the mbarrier as transaction bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, uint64_t src_gmem, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+
+// Per-warp ring state that lives across tiles (mbarrier phases must keep counting).
+struct WarpRing {
+    uint32_t data;    // shared address of stage 0
+    uint32_t bars;    // shared address of mbarrier 0
+    uint32_t slot;    // next stage to fill / drain (fill and drain advance in lock step per tile)
+    uint32_t phases;  // bit s = parity to wait for on stage s
+};
+#endif
 
 // ---- one tile = one warp ------------------------------------------------------------------------
 
@@ -218,6 +328,79 @@ __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, 
     }
 }
 
+#if MODK_BULK
+// Interior chunks through the shared-memory ring: lane 0 keeps up to kStages rounds (512 B each, +16
+// when the chunk straddles two granules) in flight with bulk-async copies; per round the warp first
+// computes its 16 keystream bytes (no memory dependence), then waits for the stage, reads its
+// granule(s) with LDS.128, funnel-shifts, XORs and stores, and finally hands the stage back to be
+// refilled kStages rounds ahead.  Loads in flight cost shared memory, not registers.
+template <int kWs>
+__device__ __forceinline__ void process_interior_bulk(const TileGeom& g, uint32_t v, const uint32_t lane,
+                                                      const uint32_t two, WarpRing& ring)
+{
+    const uint32_t bs = (g.shift & 3u) * 8u;
+    const uint32_t m_hi = min(g.c_end, g.f_hi);
+    const uint32_t lo = max(g.c_begin, g.f_lo);
+    if (lo >= m_hi)
+        return;
+    const uint32_t n_rounds = (m_hi - g.c_begin + 31u) >> 5;
+    constexpr uint32_t kExtra = (kWs >= 0) ? 1u : 0u;
+
+    auto issue = [&](uint32_t r, uint32_t stage) {
+        const uint32_t base = g.c_begin + 32u * r;
+        const uint32_t a = max(base, lo), b = min(base + 32u, m_hi);
+        if (lane == 0 && b > a) {
+            const uint32_t bytes = 16u * (b - a + kExtra);
+            const uint32_t bar = ring.bars + 8u * stage;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(ring.data + stage * kStageBytes + 16u * (a - base), g.src_al + 16ull * a, bytes, bar);
+        }
+    };
+
+    const uint32_t first_slot = ring.slot;
+    const uint32_t pre = min(n_rounds, (uint32_t)kStages);
+    for (uint32_t r = 0; r < pre; ++r)
+        issue(r, (first_slot + r) % (uint32_t)kStages);
+
+#pragma unroll 1
+    for (uint32_t r = 0; r < n_rounds; ++r) {
+        const uint32_t stage = (first_slot + r) % (uint32_t)kStages;
+        const uint32_t base = g.c_begin + 32u * r;
+        const uint32_t c = base + lane;
+        const bool fast = (c >= lo) && (c < m_hi);
+        const bool any = max(base, lo) < min(base + 32u, m_hi);  // warp-uniform: this round fetched something
+        const uint4 ks = keystream_chunk(v, two);
+        if (any) {
+            mbar_wait(ring.bars + 8u * stage, (ring.phases >> stage) & 1u);
+            ring.phases ^= 1u << stage;
+        }
+        if (fast) {
+            const uint32_t at = ring.data + stage * kStageBytes + 16u * lane;
+            uint4 data = lds128(at);
+            if (kWs >= 0) {
+                const uint4 nx = lds128(at + 16u);
+                const uint32_t w[8] = {data.x, data.y, data.z, data.w, nx.x, nx.y, nx.z, nx.w};
+                constexpr int k = kWs < 0 ? 0 : kWs;
+                data.x = __funnelshift_r(w[k + 0], w[k + 1], bs);
+                data.y = __funnelshift_r(w[k + 1], w[k + 2], bs);
+                data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
+                data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
+            }
+            data.x ^= ks.x;
+            data.y ^= ks.y;
+            data.z ^= ks.z;
+            data.w ^= ks.w;
+            stg128(g.dst_al + 16ull * c, data);
+        }
+        __syncwarp();  // every lane has consumed the stage (its LDS results fed the XOR above)
+        if (r + (uint32_t)kStages < n_rounds)
+            issue(r + (uint32_t)kStages, stage);
+        v = mulmod(v, kRoundJump);
+    }
+    ring.slot = (first_slot + n_rounds) % (uint32_t)kStages;
+}
+#endif
+
 // (negated) state just before byte (16 * tin * kChunksPerTile - h0) of an entry:
 //   n0 * a^(-h0) * a^(kTileBytes * tin)
 __device__ __forceinline__ uint32_t tile_start_state(int32_t key, uint32_t h0, uint32_t tin)
@@ -227,9 +410,19 @@ __device__ __forceinline__ uint32_t tile_start_state(int32_t key, uint32_t h0, u
     return mulmod(st, mulmod(c_tw0[tin & (uint32_t)(kTw0Size - 1)], c_tw1[tin / (uint32_t)kTw0Size]));
 }
 
+#if MODK_BULK
+#define MODK_RING_PARAM , WarpRing& ring
+#define MODK_RING_ARG , ring
+#define MODK_INTERIOR(K) process_interior_bulk<K>(g, v, lane, a.two, ring)
+#else
+#define MODK_RING_PARAM
+#define MODK_RING_ARG
+#define MODK_INTERIOR(K) process_interior<K>(g, v, lane, a.two)
+#endif
+
 __device__ __forceinline__ void run_tile(const BatchArgs& a, const uint64_t src_off, const uint64_t dst_off,
                                          const uint32_t len, const uint32_t st, const uint32_t tin,
-                                         const uint32_t lane)
+                                         const uint32_t lane MODK_RING_PARAM)
 {
     TileGeom g;
     g.len = len;
@@ -272,13 +465,13 @@ __device__ __forceinline__ void run_tile(const BatchArgs& a, const uint64_t src_
 
     const uint32_t v = mulmod(st, g_chunk_pow[lane]);
     if (g.shift == 0u) {
-        process_interior<-1>(g, v, lane, a.two);
+        MODK_INTERIOR(-1);
     } else {
         switch (g.shift >> 2) {
-        case 0: process_interior<0>(g, v, lane, a.two); break;
-        case 1: process_interior<1>(g, v, lane, a.two); break;
-        case 2: process_interior<2>(g, v, lane, a.two); break;
-        default: process_interior<3>(g, v, lane, a.two); break;
+        case 0: MODK_INTERIOR(0); break;
+        case 1: MODK_INTERIOR(1); break;
+        case 2: MODK_INTERIOR(2); break;
+        default: MODK_INTERIOR(3); break;
         }
     }
 }
@@ -297,10 +490,31 @@ __device__ __forceinline__ TileRec load_tile_rec(const TileRec* p)
     return r;
 }
 
+#if MODK_BULK
+// One ring per warp; its lane 0 initialises the mbarriers (one arrival each: the expect_tx).
+#define MODK_RING_SETUP                                                                              \
+    __shared__ __align__(128) uint8_t s_ring[kWarpsPerCta][kStages][kStageBytes];                    \
+    __shared__ __align__(8) uint64_t s_bars[kWarpsPerCta][kStages];                                  \
+    WarpRing ring;                                                                                   \
+    ring.data = smem_u32(&s_ring[threadIdx.x >> 5][0][0]);                                           \
+    ring.bars = smem_u32(&s_bars[threadIdx.x >> 5][0]);                                              \
+    ring.slot = 0;                                                                                   \
+    ring.phases = 0;                                                                                 \
+    if ((threadIdx.x & 31u) == 0) {                                                                  \
+        for (int i = 0; i < kStages; ++i)                                                            \
+            mbar_init(ring.bars + 8u * i, 1u);                                                       \
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                           \
+    }                                                                                                \
+    __syncthreads();
+#else
+#define MODK_RING_SETUP
+#endif
+
 // Persistent batched kernel: warp w of the grid takes tiles w, w + W, w + 2W, ... and loads the
 // record of its next tile before it starts streaming the current one.
 __global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_kernel(const BatchArgs a)
 {
+    MODK_RING_SETUP
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t stride = gridDim.x * (uint32_t)kWarpsPerCta;
     uint32_t tile = blockIdx.x * (uint32_t)kWarpsPerCta + (threadIdx.x >> 5);
@@ -312,7 +526,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_ker
         TileRec nxt = cur;
         if (more)
             nxt = load_tile_rec(a.tiles + tile + stride);
-        run_tile(a, cur.src_off, cur.dst_off, cur.len, cur.state, cur.tin, lane);
+        run_tile(a, cur.src_off, cur.dst_off, cur.len, cur.state, cur.tin, lane MODK_RING_ARG);
         if (!more)
             break;
         cur = nxt;
@@ -326,6 +540,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_ker
 __global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS)
 cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
 {
+    MODK_RING_SETUP
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t stride = gridDim.x * (uint32_t)kWarpsPerCta;
     for (uint32_t tile = blockIdx.x * (uint32_t)kWarpsPerCta + (threadIdx.x >> 5); tile < a.n_tiles;) {
@@ -333,7 +548,7 @@ cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
         const DevDesc& d = in.d[e];
         const uint32_t tin = tile - d.first_tile;
         const uint32_t h0 = (uint32_t)((uint64_t)a.dst + d.dst_off) & 15u;
-        run_tile(a, d.src_off, d.dst_off, d.len, tile_start_state(d.key, h0, tin), tin, lane);
+        run_tile(a, d.src_off, d.dst_off, d.len, tile_start_state(d.key, h0, tin), tin, lane MODK_RING_ARG);
         if ((a.n_tiles - tile) <= stride)
             break;
         tile += stride;
