@@ -70,6 +70,7 @@ constexpr int kTw1Size = (int)(((1ull << 32) / kTileBytes) / kTw0Size + 2);
 __constant__ uint32_t c_tw0[kTw0Size];  // a^(kTileBytes * j)
 __constant__ uint32_t c_tw1[kTw1Size];  // a^(kTileBytes * 1024 * j)
 __constant__ uint32_t c_ainv[16];       // a^(-h): rewinds the stream to the chunk grid origin
+__constant__ uint32_t c_round_pow[kIters];  // a^(512 * r): r rounds into a tile (inline kernel's short tiles)
 __device__ uint32_t g_chunk_pow[kChunksPerTile];  // a^(16 * j): lane-divergent index, so HBM/L1 rather than the constant bank
 
 constexpr uint32_t kRoundJump = modlcg::pow_a(512);  // one round = 32 lanes x 16 bytes further down the stream
@@ -421,8 +422,8 @@ __device__ __forceinline__ uint32_t tile_start_state(int32_t key, uint32_t h0, u
 #endif
 
 __device__ __forceinline__ void run_tile(const BatchArgs& a, const uint64_t src_off, const uint64_t dst_off,
-                                         const uint32_t len, const uint32_t st, const uint32_t tin,
-                                         const uint32_t lane MODK_RING_PARAM)
+                                         const uint32_t len, const uint32_t st, const uint32_t c_begin,
+                                         const uint32_t tile_chunks, const uint32_t lane MODK_RING_PARAM)
 {
     TileGeom g;
     g.len = len;
@@ -436,8 +437,8 @@ __device__ __forceinline__ void run_tile(const BatchArgs& a, const uint64_t src_
 
     const uint64_t span = (uint64_t)g.h0 + len;  // bytes from the chunk grid origin to the entry end
     const uint32_t nchunks = (uint32_t)((span + 15u) >> 4);
-    g.c_begin = tin * (uint32_t)kChunksPerTile;
-    g.c_end = min(g.c_begin + (uint32_t)kChunksPerTile, nchunks);
+    g.c_begin = c_begin;
+    g.c_end = min(c_begin + tile_chunks, nchunks);
 
     // interior chunks: all 16 destination bytes belong to the entry, and the one or two source
     // granules they need lie wholly inside the source buffer
@@ -452,11 +453,15 @@ __device__ __forceinline__ void run_tile(const BatchArgs& a, const uint64_t src_
     g.f_lo = (uint32_t)f_lo;
     g.f_hi = (uint32_t)f_hi;
 
-    // edge chunks first (rare: skipped for tiles that are interior throughout)
+    // edge chunks first (rare: skipped for tiles that are interior throughout).  The chunks below
+    // f_lo and those from f_hi on are enumerated as one compact list, one lane each, so the head
+    // and tail edge of a small entry are handled in the same pass.
     if (g.c_begin < g.f_lo || g.c_end > g.f_hi) {
-        for (uint32_t c = g.c_begin + lane; c < g.c_end; c += 32u) {
-            if (c >= g.f_lo && c < g.f_hi)
-                continue;
+        const uint32_t n_head = g.f_lo > g.c_begin ? min(g.c_end, g.f_lo) - g.c_begin : 0u;
+        const uint32_t tail0 = max(g.c_begin, g.f_hi);
+        const uint32_t n_tail = g.c_end > tail0 ? g.c_end - tail0 : 0u;
+        for (uint32_t i = lane; i < n_head + n_tail; i += 32u) {
+            const uint32_t c = i < n_head ? g.c_begin + i : tail0 + (i - n_head);
             edge_chunk(reinterpret_cast<const uint8_t*>(g.src_addr), reinterpret_cast<uint8_t*>(g.dst_addr),
                        16ll * (long long)c - (long long)g.h0, g.len,
                        mulmod(st, g_chunk_pow[c - g.c_begin]), a.two);
@@ -526,7 +531,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_ker
         TileRec nxt = cur;
         if (more)
             nxt = load_tile_rec(a.tiles + tile + stride);
-        run_tile(a, cur.src_off, cur.dst_off, cur.len, cur.state, cur.tin, lane MODK_RING_ARG);
+        run_tile(a, cur.src_off, cur.dst_off, cur.len, cur.state, cur.tin * (uint32_t)kChunksPerTile,
+                 (uint32_t)kChunksPerTile, lane MODK_RING_ARG);
         if (!more)
             break;
         cur = nxt;
@@ -546,9 +552,13 @@ cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
     for (uint32_t tile = blockIdx.x * (uint32_t)kWarpsPerCta + (threadIdx.x >> 5); tile < a.n_tiles;) {
         const uint32_t e = tile / a.tiles_per_entry;
         const DevDesc& d = in.d[e];
-        const uint32_t tin = tile - d.first_tile;
+        // inline tiles are a.rounds_per_tile rounds long (short buffers are spread over more warps):
+        // start from the enclosing full-size tile's state and jump the remaining rounds
+        const uint32_t round0 = (tile - d.first_tile) * a.rounds_per_tile;
         const uint32_t h0 = (uint32_t)((uint64_t)a.dst + d.dst_off) & 15u;
-        run_tile(a, d.src_off, d.dst_off, d.len, tile_start_state(d.key, h0, tin), tin, lane MODK_RING_ARG);
+        const uint32_t st = mulmod(tile_start_state(d.key, h0, round0 / (uint32_t)kIters),
+                                   c_round_pow[round0 % (uint32_t)kIters]);
+        run_tile(a, d.src_off, d.dst_off, d.len, st, round0 * 32u, a.rounds_per_tile * 32u, lane MODK_RING_ARG);
         if ((a.n_tiles - tile) <= stride)
             break;
         tile += stride;
@@ -587,7 +597,7 @@ __global__ void build_tiles_kernel(const DevDesc* __restrict__ descs, uint32_t n
 
 cudaError_t upload_tables()
 {
-    static uint32_t h_tw0[kTw0Size], h_tw1[kTw1Size], h_ainv[16], h_chunk[kChunksPerTile];
+    static uint32_t h_tw0[kTw0Size], h_tw1[kTw1Size], h_ainv[16], h_chunk[kChunksPerTile], h_round[kIters];
     static bool built = false;
     if (!built) {
         for (int j = 0; j < kTw0Size; ++j)
@@ -598,6 +608,8 @@ cudaError_t upload_tables()
             h_ainv[h] = modlcg::pow_a_inv((uint64_t)h);
         for (int j = 0; j < kChunksPerTile; ++j)
             h_chunk[j] = modlcg::pow_a(16ull * (uint64_t)j);
+        for (int r = 0; r < kIters; ++r)
+            h_round[r] = modlcg::pow_a(512ull * (uint64_t)r);
         built = true;
     }
     cudaError_t err;
@@ -605,6 +617,7 @@ cudaError_t upload_tables()
     if ((err = cudaMemcpyToSymbol(c_tw1, h_tw1, sizeof(h_tw1))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_ainv, h_ainv, sizeof(h_ainv))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(g_chunk_pow, h_chunk, sizeof(h_chunk))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(c_round_pow, h_round, sizeof(h_round))) != cudaSuccess) return err;
     return cudaSuccess;
 }
 

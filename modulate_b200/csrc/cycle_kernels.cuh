@@ -51,6 +51,7 @@ struct BatchArgs {
     const TileRec* tiles;  // HBM tile records (nullptr in inline mode)
     uint32_t n_tiles;
     uint32_t tiles_per_entry;  // inline mode: entry = tile / tiles_per_entry
+    uint32_t rounds_per_tile = kIters;  // inline mode: tile length in rounds of 32 chunks (a divisor of kIters)
     // 16-byte granules of the source may be loaded whole only inside [src_lo16, src_hi16).
     uint64_t src_lo16;
     uint64_t src_hi16;
@@ -59,12 +60,13 @@ struct BatchArgs {
 
 // Number of tiles an entry of `len` bytes occupies when its first destination byte sits at
 // (address & 15) == h0.
-__host__ __device__ inline uint32_t tiles_for_entry(uint32_t h0, uint32_t len)
+__host__ __device__ inline uint32_t tiles_for_entry(uint32_t h0, uint32_t len,
+                                                    uint32_t chunks_per_tile = (uint32_t)kChunksPerTile)
 {
     if (len == 0)
         return 0;
     const uint64_t chunks = ((uint64_t)h0 + len + 15u) >> 4;
-    return (uint32_t)((chunks + kChunksPerTile - 1) / kChunksPerTile);
+    return (uint32_t)((chunks + chunks_per_tile - 1) / chunks_per_tile);
 }
 
 cudaError_t upload_tables();  // jump tables -> __constant__ / global memory of the current device

@@ -175,7 +175,18 @@ int launch_contiguous(const uint8_t* d_src, uint8_t* d_dst, uint64_t len, int32_
     uint64_t piece = kMaxPiece;
     const uint64_t src_lo16 = ((uint64_t)(uintptr_t)d_src + 15u) & ~15ull;
     const uint64_t src_hi16 = ((uint64_t)(uintptr_t)d_src + len) & ~15ull;
-    const uint32_t tpe = modk::tiles_for_entry(h0, (uint32_t)piece);
+    // short buffers use shorter tiles so that they still spread over the whole GPU: halve the tile
+    // until there is at least one tile per resident warp or a tile is a single round
+    uint32_t rounds = (uint32_t)modk::kIters;
+    {
+        int grid_cap = 0;
+        CUDA_TRY(modk::persistent_grid(&grid_cap));
+        const uint64_t want_tiles = (uint64_t)grid_cap * modk::kWarpsPerCta;
+        while (rounds > 1 && (len + 512ull * rounds - 1) / (512ull * rounds) < want_tiles)
+            rounds >>= 1;
+    }
+    const uint32_t cpt = 32u * rounds;  // chunks per tile
+    const uint32_t tpe = modk::tiles_for_entry(h0, (uint32_t)piece, cpt);
     uint64_t done = 0;
     uint32_t k0 = modlcg::key_residue(key);
     while (done < len) {
@@ -192,7 +203,7 @@ int launch_contiguous(const uint8_t* d_src, uint8_t* d_dst, uint64_t len, int32_
             d.key = (int32_t)modlcg::mulmod(k0, modlcg::pow_a(done));
             d.first_tile = n * tpe;
             d.pad = 0;
-            tiles = n * tpe + modk::tiles_for_entry(h0, (uint32_t)this_len);
+            tiles = n * tpe + modk::tiles_for_entry(h0, (uint32_t)this_len, cpt);
             done += this_len;
             ++n;
         }
@@ -201,6 +212,7 @@ int launch_contiguous(const uint8_t* d_src, uint8_t* d_dst, uint64_t len, int32_
         args.tiles = nullptr;
         args.n_tiles = tiles;
         args.tiles_per_entry = tpe;
+        args.rounds_per_tile = rounds;
         args.src_lo16 = src_lo16;
         args.src_hi16 = src_hi16;
         CUDA_TRY(modk::launch_batch_inline(args, in, stream));
