@@ -62,6 +62,14 @@ struct Context {
     uint64_t ws_src_bytes = 0;
     void* ws_dst = nullptr;
     uint64_t ws_dst_bytes = 0;
+    // plan scratch of the host-pointer batch path: pinned staging for descriptors, HBM descriptors + tiles
+    void* h_descs = nullptr;
+    uint64_t h_descs_bytes = 0;
+    void* ws_descs = nullptr;
+    uint64_t ws_descs_bytes = 0;
+    void* ws_tiles = nullptr;
+    uint64_t ws_tiles_bytes = 0;
+    cudaEvent_t plan_ready = nullptr;
 };
 
 Context g_ctx;
@@ -93,6 +101,18 @@ void release_workspaces_locked()
         cudaFree(g_ctx.ws_dst);
     g_ctx.ws_src = g_ctx.ws_dst = nullptr;
     g_ctx.ws_src_bytes = g_ctx.ws_dst_bytes = 0;
+    if (g_ctx.ws_descs)
+        cudaFree(g_ctx.ws_descs);
+    if (g_ctx.ws_tiles)
+        cudaFree(g_ctx.ws_tiles);
+    if (g_ctx.h_descs)
+        cudaFreeHost(g_ctx.h_descs);
+    g_ctx.ws_descs = g_ctx.ws_tiles = g_ctx.h_descs = nullptr;
+    g_ctx.ws_descs_bytes = g_ctx.ws_tiles_bytes = g_ctx.h_descs_bytes = 0;
+    if (g_ctx.plan_ready) {
+        cudaEventDestroy(g_ctx.plan_ready);
+        g_ctx.plan_ready = nullptr;
+    }
     if (g_ctx.streams_ready) {
         for (int i = 0; i < kPipeSlots; ++i)
             cudaStreamDestroy(g_ctx.pipe_stream[i]);
@@ -218,6 +238,56 @@ int launch_contiguous(const uint8_t* d_src, uint8_t* d_dst, uint64_t len, int32_
         CUDA_TRY(modk::launch_batch_inline(args, in, stream));
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
+    return MOD_OK;
+}
+
+// Validate descriptors against the buffer sizes and expand them into device descriptors with their
+// first-tile prefix.  Shared by mod_plan_create and the host-pointer batch path.
+int expand_descs(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint64_t dst_bytes, uint32_t dst_align,
+                 modk::DevDesc* out, uint64_t* tiles_out, uint64_t* payload_out)
+{
+    uint64_t tiles = 0, payload = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const mod_desc& d = descs[i];
+        if (d.src_off > src_bytes || (uint64_t)d.len > src_bytes - d.src_off)
+            return fail(MOD_ERR_ARG, "descriptor %llu: source range [%llu, +%u) leaves the %llu-byte buffer",
+                        (unsigned long long)i, (unsigned long long)d.src_off, d.len, (unsigned long long)src_bytes);
+        if (d.dst_off > dst_bytes || (uint64_t)d.len > dst_bytes - d.dst_off)
+            return fail(MOD_ERR_ARG, "descriptor %llu: destination range [%llu, +%u) leaves the %llu-byte buffer",
+                        (unsigned long long)i, (unsigned long long)d.dst_off, d.len, (unsigned long long)dst_bytes);
+        modk::DevDesc& o = out[i];
+        o.src_off = d.src_off;
+        o.dst_off = d.dst_off;
+        o.len = d.len;
+        o.key = d.key;
+        o.first_tile = (uint32_t)tiles;
+        o.pad = 0;
+        tiles += modk::tiles_for_entry((uint32_t)((dst_align + d.dst_off) & 15u), d.len);
+        payload += d.len;
+        if (tiles >= 0xFFFFFFFFull)
+            return fail(MOD_ERR_ARG, "batch too large (tile count overflows 32 bits)");
+    }
+    *tiles_out = tiles;
+    *payload_out = payload;
+    return MOD_OK;
+}
+
+int grow_pinned(void** buf, uint64_t* have, uint64_t need)
+{
+    if (*have >= need)
+        return MOD_OK;
+    if (*buf) {
+        CUDA_TRY(cudaFreeHost(*buf));
+        *buf = nullptr;
+        *have = 0;
+    }
+    need = (need + 4095) & ~4095ull;
+    cudaError_t e = cudaHostAlloc(buf, need, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MOD_ERR_NOMEM, "cudaHostAlloc(%llu) failed: %s", (unsigned long long)need, cudaGetErrorString(e));
+    }
+    *have = need;
     return MOD_OK;
 }
 
@@ -425,26 +495,8 @@ int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint6
         return fail(MOD_ERR_NOMEM, "mod_plan_create: host allocation of %llu descriptors failed", (unsigned long long)n);
     }
     uint64_t tiles = 0, payload = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        const mod_desc& d = descs[i];
-        if (d.src_off > src_bytes || (uint64_t)d.len > src_bytes - d.src_off)
-            return fail(MOD_ERR_ARG, "descriptor %llu: source range [%llu, +%u) leaves the %llu-byte buffer",
-                        (unsigned long long)i, (unsigned long long)d.src_off, d.len, (unsigned long long)src_bytes);
-        if (d.dst_off > dst_bytes || (uint64_t)d.len > dst_bytes - d.dst_off)
-            return fail(MOD_ERR_ARG, "descriptor %llu: destination range [%llu, +%u) leaves the %llu-byte buffer",
-                        (unsigned long long)i, (unsigned long long)d.dst_off, d.len, (unsigned long long)dst_bytes);
-        modk::DevDesc& o = host[i];
-        o.src_off = d.src_off;
-        o.dst_off = d.dst_off;
-        o.len = d.len;
-        o.key = d.key;
-        o.first_tile = (uint32_t)tiles;
-        o.pad = 0;
-        tiles += modk::tiles_for_entry((uint32_t)((dst_align + d.dst_off) & 15u), d.len);
-        payload += d.len;
-        if (tiles >= 0xFFFFFFFFull)
-            return fail(MOD_ERR_ARG, "mod_plan_create: batch too large (tile count overflows 32 bits)");
-    }
+    if ((rc = expand_descs(descs, n, src_bytes, dst_bytes, dst_align, host.data(), &tiles, &payload)) != MOD_OK)
+        return rc;
 
     mod_plan* p = new (std::nothrow) mod_plan();
     if (!p)
@@ -561,21 +613,39 @@ int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t
     // runs it covers, on stream g % kPipeSlots -- so the upload of one group, the kernel of another
     // and the download of a third overlap.  Only bytes covered by descriptors are written back,
     // so untouched bytes of dst survive exactly like with the reference's per-entry fwrite/fread.
+    // The plan lives in grow-only scratch (pinned staging + HBM) and is built asynchronously on pipe
+    // stream 0; the other streams wait on an event before their first kernel, the host never does.
     const bool trace = env_u64("MOD_TRACE", 0) != 0;
     const double t_begin = now_ms();
-    rc = mod_plan_create(descs, n, src_bytes, dst_bytes, 0, &plan);
-    if (rc != MOD_OK)
-        return rc;
-    const double t_plan = now_ms();
+    if (n >= 0xFFFFFFFFull)
+        return fail(MOD_ERR_ARG, "mod_cycle_batch: too many descriptors (%llu)", (unsigned long long)n);
     std::lock_guard<std::mutex> lock(g_ctx.mu);
-    auto done = [&](int code) {
-        mod_plan_destroy(plan);
-        return code;
-    };
+    auto done = [&](int code) { return code; };
+    if ((rc = grow_pinned(&g_ctx.h_descs, &g_ctx.h_descs_bytes, n * sizeof(modk::DevDesc))) != MOD_OK)
+        return rc;
+    uint64_t plan_tiles = 0, plan_payload = 0;
+    if ((rc = expand_descs(descs, n, src_bytes, dst_bytes, 0, (modk::DevDesc*)g_ctx.h_descs, &plan_tiles, &plan_payload)) != MOD_OK)
+        return rc;
+    if (plan_tiles == 0)
+        return MOD_OK;
+    if ((rc = grow(&g_ctx.ws_descs, &g_ctx.ws_descs_bytes, n * sizeof(modk::DevDesc))) != MOD_OK)
+        return rc;
+    if ((rc = grow(&g_ctx.ws_tiles, &g_ctx.ws_tiles_bytes, plan_tiles * sizeof(modk::TileRec))) != MOD_OK)
+        return rc;
     if ((rc = grow(&g_ctx.ws_src, &g_ctx.ws_src_bytes, src_bytes)) != MOD_OK)
-        return done(rc);
+        return rc;
     if ((rc = grow(&g_ctx.ws_dst, &g_ctx.ws_dst_bytes, dst_bytes)) != MOD_OK)
-        return done(rc);
+        return rc;
+    if (!g_ctx.plan_ready)
+        CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.plan_ready, cudaEventDisableTiming));
+    CUDA_TRY(cudaMemcpyAsync(g_ctx.ws_descs, g_ctx.h_descs, n * sizeof(modk::DevDesc), cudaMemcpyHostToDevice,
+                             g_ctx.pipe_stream[0]));
+    CUDA_TRY(modk::launch_build_tiles((const modk::DevDesc*)g_ctx.ws_descs, (uint32_t)n, 0, (modk::TileRec*)g_ctx.ws_tiles,
+                                      (uint32_t)plan_tiles, g_ctx.pipe_stream[0]));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaEventRecord(g_ctx.plan_ready, g_ctx.pipe_stream[0]));
+    const modk::TileRec* d_tiles = (const modk::TileRec*)g_ctx.ws_tiles;
+    const double t_plan = now_ms();
 
     struct Group {
         uint64_t e0, e1;        // descriptor range
@@ -612,7 +682,7 @@ int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t
     for (const Group& g : groups)
         window_sum += g.s_hi - g.s_lo;
     if (window_sum > src_bytes + src_bytes / 4 + (1 << 20)) {
-        Group all{0, n, 0, plan->n_tiles, 0, src_bytes};
+        Group all{0, n, 0, (uint32_t)plan_tiles, 0, src_bytes};
         groups.assign(1, all);
     }
 
@@ -695,7 +765,7 @@ int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t
         }
     }
     if (holes) {
-        Group all{0, n, 0, plan->n_tiles, 0, src_bytes};
+        Group all{0, n, 0, (uint32_t)plan_tiles, 0, src_bytes};
         groups.assign(1, all);
     }
 
@@ -716,7 +786,12 @@ int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t
         modk::BatchArgs args;
         args.src = (const uint8_t*)g_ctx.ws_src;
         args.dst = (uint8_t*)g_ctx.ws_dst;
-        args.tiles = plan->d_tiles + g.t0;
+        if (gi > 0 && gi < (size_t)kPipeSlots) {  // first use of this stream: the plan must be complete
+            e = cudaStreamWaitEvent(s, g_ctx.plan_ready, 0);
+            if (e != cudaSuccess)
+                break;
+        }
+        args.tiles = d_tiles + g.t0;
         args.n_tiles = g.t1 - g.t0;
         args.tiles_per_entry = 0;
         args.src_lo16 = src_lo16;
