@@ -44,6 +44,12 @@ using modlcg::low8_canonical;
 #ifndef MODK_MIN_CTAS
 #define MODK_MIN_CTAS 4          // resident CTAs per SM requested through __launch_bounds__ (64 registers)
 #endif
+#ifndef MODK_L2_PREFETCH
+#define MODK_L2_PREFETCH 0       // bulk L2 prefetch distance in load groups (cp.async.bulk.prefetch.L2 by lane 0); 0 = off: measured slower
+#endif
+#ifndef MODK_PF_NEXT
+#define MODK_PF_NEXT 0           // with MODK_L2_PREFETCH: also prefetch the head of the warp's next tile (measured slower)
+#endif
 #ifndef MODK_SPECULATE
 #define MODK_SPECULATE 1         // pack low bytes from lazy states, redo the ~1/8000 chunks that needed a canonical subtract
 #endif
@@ -99,6 +105,14 @@ __device__ __forceinline__ void stg128(uint64_t addr, const uint4& v)
         asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
     else
         asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+
+// Ask the memory system to bring [addr, addr + bytes) into L2 (16-byte granularity): one
+// instruction from one lane covers a whole group of rounds and costs no registers, so the LDG.128s
+// that follow a few hundred cycles later find their lines in L2 instead of paying the HBM latency.
+__device__ __forceinline__ void bulk_prefetch_l2(uint64_t addr, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
 }
 
 // ---- per-chunk arithmetic -------------------------------------------------------------------
@@ -241,6 +255,15 @@ struct WarpRing {
 
 // ---- one tile = one warp ------------------------------------------------------------------------
 
+// Where this warp's NEXT tile starts reading, so that its first load group can be pulled into L2
+// while the current tile is still being ciphered (the fields alias the prefetched tile record and
+// are only touched one load group into the current tile, when that record has arrived).
+struct NextHead {
+    uint64_t src_off;
+    uint32_t tin;
+    bool valid;
+};
+
 struct TileGeom {
     uint64_t dst_al;    // 16-byte aligned address of chunk 0
     uint64_t src_al;    // 16-byte aligned address of the granule holding chunk 0's first source byte
@@ -283,16 +306,38 @@ __device__ __noinline__ void edge_chunk(const uint8_t* src_entry, uint8_t* dst_e
 // starts kWs words (+ a runtime 0..3 bytes) into its first granule and straddles two.
 template <int kWs>
 __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, const uint32_t lane,
-                                                 const uint32_t two)
+                                                 const uint32_t two, const BatchArgs& a, const NextHead& nh)
 {
     const uint32_t bs = (g.shift & 3u) * 8u;
     const uint32_t m_hi = min(g.c_end, g.f_hi);
 
+    constexpr uint32_t kGroupChunks = 32u * kUnroll;
+    if (MODK_L2_PREFETCH > 1 && lane == 0) {  // groups 1 .. distance-1 of this tile (group 0 is loaded right away)
+        const uint32_t c0 = g.c_begin + kGroupChunks;
+        if (c0 < m_hi)
+            bulk_prefetch_l2(g.src_al + 16ull * c0,
+                             16u * (min(m_hi - c0, (uint32_t)(MODK_L2_PREFETCH - 1) * kGroupChunks) + (kWs >= 0 ? 1u : 0u)));
+    }
+
 #pragma unroll 1
-    for (uint32_t base = g.c_begin; base < m_hi; base += 32u * kUnroll) {
+    for (uint32_t base = g.c_begin; base < m_hi; base += kGroupChunks) {
         uint4 own[kUnroll];
         uint4 nxt[kUnroll];
         bool fast[kUnroll];
+
+        if (MODK_L2_PREFETCH > 0 && lane == 0) {
+            const uint32_t c0 = base + (uint32_t)MODK_L2_PREFETCH * kGroupChunks;
+            if (c0 < m_hi)
+                bulk_prefetch_l2(g.src_al + 16ull * c0, 16u * (min(m_hi - c0, kGroupChunks) + (kWs >= 0 ? 1u : 0u)));
+            if (MODK_PF_NEXT && nh.valid && base == g.c_begin + kGroupChunks) {  // second group: the next record is here by now
+                uint64_t lo = ((uint64_t)a.src + nh.src_off + (uint64_t)nh.tin * kTileBytes) & ~15ull;
+                lo = lo > a.src_lo16 ? lo : a.src_lo16;
+                const uint64_t want = lo + 16ull * ((uint64_t)MODK_L2_PREFETCH * kGroupChunks + 2ull);
+                const uint64_t hi = want < a.src_hi16 ? want : a.src_hi16;
+                if (hi > lo)
+                    bulk_prefetch_l2(lo, (uint32_t)(hi - lo));
+            }
+        }
 
         // phase 1: every load of the unrolled group is issued before anything consumes one
 #pragma unroll
@@ -418,12 +463,12 @@ __device__ __forceinline__ uint32_t tile_start_state(int32_t key, uint32_t h0, u
 #else
 #define MODK_RING_PARAM
 #define MODK_RING_ARG
-#define MODK_INTERIOR(K) process_interior<K>(g, v, lane, a.two)
+#define MODK_INTERIOR(K) process_interior<K>(g, v, lane, a.two, a, nh)
 #endif
 
 __device__ __forceinline__ void run_tile(const BatchArgs& a, const uint64_t src_off, const uint64_t dst_off,
                                          const uint32_t len, const uint32_t st, const uint32_t c_begin,
-                                         const uint32_t tile_chunks, const uint32_t lane MODK_RING_PARAM)
+                                         const uint32_t tile_chunks, const uint32_t lane, const NextHead& nh MODK_RING_PARAM)
 {
     TileGeom g;
     g.len = len;
@@ -531,8 +576,9 @@ __global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_ker
         TileRec nxt = cur;
         if (more)
             nxt = load_tile_rec(a.tiles + tile + stride);
+        const NextHead nh{nxt.src_off, nxt.tin, more};
         run_tile(a, cur.src_off, cur.dst_off, cur.len, cur.state, cur.tin * (uint32_t)kChunksPerTile,
-                 (uint32_t)kChunksPerTile, lane MODK_RING_ARG);
+                 (uint32_t)kChunksPerTile, lane, nh MODK_RING_ARG);
         if (!more)
             break;
         cur = nxt;
@@ -558,7 +604,8 @@ cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
         const uint32_t h0 = (uint32_t)((uint64_t)a.dst + d.dst_off) & 15u;
         const uint32_t st = mulmod(tile_start_state(d.key, h0, round0 / (uint32_t)kIters),
                                    c_round_pow[round0 % (uint32_t)kIters]);
-        run_tile(a, d.src_off, d.dst_off, d.len, st, round0 * 32u, a.rounds_per_tile * 32u, lane MODK_RING_ARG);
+        const NextHead nh{0ull, 0u, false};
+        run_tile(a, d.src_off, d.dst_off, d.len, st, round0 * 32u, a.rounds_per_tile * 32u, lane, nh MODK_RING_ARG);
         if ((a.n_tiles - tile) <= stride)
             break;
         tile += stride;
