@@ -376,6 +376,17 @@ def run_gpu_arm(args) -> None:
                 "traffic": None, "kernel": "modk::cycle_batch_kernel", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": 2 * payload, "peak_source": peak_src,
                 "payload_gbs": payload / (kernel_ms * 1e-3) / 1e9}
+    # the co-limiting integer roofline: one IMAD.WIDE per payload byte at the measured issue rate
+    try:
+        with open(os.path.join(ROOT, "profiles", "imad.json")) as f:
+            lanes = float(json.load(f)["imad_wide_thread_instr_per_clk_per_sm"])
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        mhz = clock_info.get("sm_mhz") or clock_info.get("sm_max_mhz") or 1965.0
+        imad_peak = sm_count * lanes * mhz * 1e6 / 1e9  # payload GB/s if IMAD.WIDE were the only limit
+        roofline["imad"] = {"peak_payload_gbs": imad_peak, "frac": roofline["payload_gbs"] / imad_peak,
+                            "imad_wide_per_clk_per_sm": lanes, "note": "HBM is the binding roofline"}
+    except Exception:
+        pass
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
