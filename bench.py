@@ -105,7 +105,7 @@ class ClockSampler:
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
     def __init__(self, index: int, period_s: float = 0.004):
-        self.samples, self.reasons = [], set()
+        self.samples, self.reasons, self.power = [], set(), []
         self.max_mhz = None
         self.period = period_s
         self._stop = threading.Event()
@@ -130,6 +130,7 @@ class ClockSampler:
                 for bit, name in self.REASONS.items():
                     if mask & bit and name != "gpu_idle":
                         self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
             time.sleep(self.period)
@@ -145,7 +146,7 @@ class ClockSampler:
             self._thread.join(timeout=2)
         med = float(np.median(self.samples)) if self.samples else None
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
 
 
 # ---- CPU arm: the unmodified reference cipher on the host cores ------------------------------------
@@ -440,7 +441,7 @@ def run_gpu_arm(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])

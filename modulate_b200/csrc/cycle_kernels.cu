@@ -44,11 +44,8 @@ using modlcg::low8_canonical;
 #ifndef MODK_MIN_CTAS
 #define MODK_MIN_CTAS 4          // resident CTAs per SM requested through __launch_bounds__ (64 registers)
 #endif
-#ifndef MODK_L2_PREFETCH
-#define MODK_L2_PREFETCH 0       // bulk L2 prefetch distance in load groups (cp.async.bulk.prefetch.L2 by lane 0); 0 = off: measured slower
-#endif
-#ifndef MODK_PF_NEXT
-#define MODK_PF_NEXT 0           // with MODK_L2_PREFETCH: also prefetch the head of the warp's next tile (measured slower)
+#ifndef MODK_FULL_GROUPS
+#define MODK_FULL_GROUPS 1       // predicate-free code path for load groups that are interior throughout
 #endif
 #ifndef MODK_SPECULATE
 #define MODK_SPECULATE 1         // pack low bytes from lazy states, redo the ~1/8000 chunks that needed a canonical subtract
@@ -105,14 +102,6 @@ __device__ __forceinline__ void stg128(uint64_t addr, const uint4& v)
         asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
     else
         asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
-}
-
-// Ask the memory system to bring [addr, addr + bytes) into L2 (16-byte granularity): one
-// instruction from one lane covers a whole group of rounds and costs no registers, so the LDG.128s
-// that follow a few hundred cycles later find their lines in L2 instead of paying the HBM latency.
-__device__ __forceinline__ void bulk_prefetch_l2(uint64_t addr, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(addr), "r"(bytes) : "memory");
 }
 
 // ---- per-chunk arithmetic -------------------------------------------------------------------
@@ -255,15 +244,6 @@ struct WarpRing {
 
 // ---- one tile = one warp ------------------------------------------------------------------------
 
-// Where this warp's NEXT tile starts reading, so that its first load group can be pulled into L2
-// while the current tile is still being ciphered (the fields alias the prefetched tile record and
-// are only touched one load group into the current tile, when that record has arrived).
-struct NextHead {
-    uint64_t src_off;
-    uint32_t tin;
-    bool valid;
-};
-
 struct TileGeom {
     uint64_t dst_al;    // 16-byte aligned address of chunk 0
     uint64_t src_al;    // 16-byte aligned address of the granule holding chunk 0's first source byte
@@ -300,78 +280,78 @@ __device__ __noinline__ void edge_chunk(const uint8_t* src_entry, uint8_t* dst_e
 
 // Interior chunks of the tile: kUnroll independent chunks in flight per thread (all loads of a
 // group are issued before any is consumed).  A register ping-pong that issued the next group's
-// loads before ciphering the current one measured SLOWER on B200 (profiles/r01_tuning.md), so the
-// simple form stays: latency is covered by the 32 resident warps per SM.
+// loads before ciphering the current one, a bulk-async shared-memory ring and bulk L2 prefetches
+// all measured SLOWER on B200 (profiles/r01_tuning.md), so the simple form stays: latency is
+// covered by the 32 resident warps per SM.
 // kWs < 0: source and destination are co-aligned (one load per chunk).  kWs in 0..3: the chunk
 // starts kWs words (+ a runtime 0..3 bytes) into its first granule and straddles two.
+// kFull: every chunk of the group is interior, so there are no per-lane predicates and all
+// addresses are one 64-bit pointer per lane plus immediates.
+template <int kWs, bool kFull>
+__device__ __forceinline__ uint32_t cipher_group(const TileGeom& g, const uint32_t base, const uint32_t m_hi,
+                                                 uint32_t v, const uint32_t lane, const uint32_t bs,
+                                                 const uint32_t two)
+{
+    uint4 own[kUnroll];
+    uint4 nxt[kUnroll];
+    bool fast[kUnroll];
+    const uint64_t sp = g.src_al + 16ull * (base + lane);
+    const uint64_t dp = g.dst_al + 16ull * (base + lane);
+
+    // phase 1: every load of the unrolled group is issued before anything consumes one
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        const uint32_t c = base + (uint32_t)u * 32u + lane;
+        fast[u] = kFull || ((c >= g.f_lo) && (c < m_hi));
+        own[u] = make_uint4(0u, 0u, 0u, 0u);
+        nxt[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (fast[u]) {
+            own[u] = ldg128<(kWs < 0)>(sp + 512ull * u);
+            if (kWs >= 0)
+                nxt[u] = ldg128<false>(sp + 512ull * u + 16ull);
+        }
+    }
+
+    // phase 2: re-align, cipher, store
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        uint4 data = own[u];
+        if (kWs >= 0) {
+            const uint32_t w[8] = {own[u].x, own[u].y, own[u].z, own[u].w, nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
+            constexpr int k = kWs < 0 ? 0 : kWs;
+            data.x = __funnelshift_r(w[k + 0], w[k + 1], bs);
+            data.y = __funnelshift_r(w[k + 1], w[k + 2], bs);
+            data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
+            data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
+        }
+        if (fast[u])
+            stg128(dp + 512ull * u, cycle_chunk(data, v, two));
+        v = mulmod(v, kRoundJump);  // state just before this lane's chunk of the next round
+    }
+    return v;
+}
+
 template <int kWs>
 __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, const uint32_t lane,
-                                                 const uint32_t two, const BatchArgs& a, const NextHead& nh)
+                                                 const uint32_t two)
 {
     const uint32_t bs = (g.shift & 3u) * 8u;
     const uint32_t m_hi = min(g.c_end, g.f_hi);
-
     constexpr uint32_t kGroupChunks = 32u * kUnroll;
-    if (MODK_L2_PREFETCH > 1 && lane == 0) {  // groups 1 .. distance-1 of this tile (group 0 is loaded right away)
-        const uint32_t c0 = g.c_begin + kGroupChunks;
-        if (c0 < m_hi)
-            bulk_prefetch_l2(g.src_al + 16ull * c0,
-                             16u * (min(m_hi - c0, (uint32_t)(MODK_L2_PREFETCH - 1) * kGroupChunks) + (kWs >= 0 ? 1u : 0u)));
-    }
 
+    uint32_t base = g.c_begin;
+    if (MODK_FULL_GROUPS && kWs < 0) {  // co-aligned variant only: four more copies would overflow the I-cache
+        if (base < g.f_lo && base < m_hi) {  // the group holding the entry's head edge
+            v = cipher_group<kWs, false>(g, base, m_hi, v, lane, bs, two);
+            base += kGroupChunks;
+        }
 #pragma unroll 1
-    for (uint32_t base = g.c_begin; base < m_hi; base += kGroupChunks) {
-        uint4 own[kUnroll];
-        uint4 nxt[kUnroll];
-        bool fast[kUnroll];
-
-        if (MODK_L2_PREFETCH > 0 && lane == 0) {
-            const uint32_t c0 = base + (uint32_t)MODK_L2_PREFETCH * kGroupChunks;
-            if (c0 < m_hi)
-                bulk_prefetch_l2(g.src_al + 16ull * c0, 16u * (min(m_hi - c0, kGroupChunks) + (kWs >= 0 ? 1u : 0u)));
-            if (MODK_PF_NEXT && nh.valid && base == g.c_begin + kGroupChunks) {  // second group: the next record is here by now
-                uint64_t lo = ((uint64_t)a.src + nh.src_off + (uint64_t)nh.tin * kTileBytes) & ~15ull;
-                lo = lo > a.src_lo16 ? lo : a.src_lo16;
-                const uint64_t want = lo + 16ull * ((uint64_t)MODK_L2_PREFETCH * kGroupChunks + 2ull);
-                const uint64_t hi = want < a.src_hi16 ? want : a.src_hi16;
-                if (hi > lo)
-                    bulk_prefetch_l2(lo, (uint32_t)(hi - lo));
-            }
-        }
-
-        // phase 1: every load of the unrolled group is issued before anything consumes one
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const uint32_t c = base + (uint32_t)u * 32u + lane;
-            fast[u] = (c >= g.f_lo) && (c < m_hi);
-            own[u] = make_uint4(0u, 0u, 0u, 0u);
-            nxt[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (fast[u]) {
-                own[u] = ldg128<(kWs < 0)>(g.src_al + 16ull * c);
-                if (kWs >= 0)
-                    nxt[u] = ldg128<false>(g.src_al + 16ull * c + 16ull);
-            }
-        }
-
-        // phase 2: re-align, cipher, store
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const uint32_t c = base + (uint32_t)u * 32u + lane;
-            uint4 data = own[u];
-            if (kWs >= 0) {
-                const uint32_t w[8] = {own[u].x, own[u].y, own[u].z, own[u].w,
-                                       nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
-                constexpr int k = kWs < 0 ? 0 : kWs;
-                data.x = __funnelshift_r(w[k + 0], w[k + 1], bs);
-                data.y = __funnelshift_r(w[k + 1], w[k + 2], bs);
-                data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
-                data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
-            }
-            if (fast[u])
-                stg128(g.dst_al + 16ull * c, cycle_chunk(data, v, two));
-            v = mulmod(v, kRoundJump);  // state just before this lane's chunk of the next round
-        }
+        for (; base + kGroupChunks <= m_hi; base += kGroupChunks)
+            v = cipher_group<kWs, true>(g, base, m_hi, v, lane, bs, two);
     }
+#pragma unroll 1
+    for (; base < m_hi; base += kGroupChunks)
+        v = cipher_group<kWs, false>(g, base, m_hi, v, lane, bs, two);
 }
 
 #if MODK_BULK
@@ -463,12 +443,12 @@ __device__ __forceinline__ uint32_t tile_start_state(int32_t key, uint32_t h0, u
 #else
 #define MODK_RING_PARAM
 #define MODK_RING_ARG
-#define MODK_INTERIOR(K) process_interior<K>(g, v, lane, a.two, a, nh)
+#define MODK_INTERIOR(K) process_interior<K>(g, v, lane, a.two)
 #endif
 
 __device__ __forceinline__ void run_tile(const BatchArgs& a, const uint64_t src_off, const uint64_t dst_off,
                                          const uint32_t len, const uint32_t st, const uint32_t c_begin,
-                                         const uint32_t tile_chunks, const uint32_t lane, const NextHead& nh MODK_RING_PARAM)
+                                         const uint32_t tile_chunks, const uint32_t lane MODK_RING_PARAM)
 {
     TileGeom g;
     g.len = len;
@@ -576,9 +556,8 @@ __global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_ker
         TileRec nxt = cur;
         if (more)
             nxt = load_tile_rec(a.tiles + tile + stride);
-        const NextHead nh{nxt.src_off, nxt.tin, more};
         run_tile(a, cur.src_off, cur.dst_off, cur.len, cur.state, cur.tin * (uint32_t)kChunksPerTile,
-                 (uint32_t)kChunksPerTile, lane, nh MODK_RING_ARG);
+                 (uint32_t)kChunksPerTile, lane MODK_RING_ARG);
         if (!more)
             break;
         cur = nxt;
@@ -604,8 +583,7 @@ cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
         const uint32_t h0 = (uint32_t)((uint64_t)a.dst + d.dst_off) & 15u;
         const uint32_t st = mulmod(tile_start_state(d.key, h0, round0 / (uint32_t)kIters),
                                    c_round_pow[round0 % (uint32_t)kIters]);
-        const NextHead nh{0ull, 0u, false};
-        run_tile(a, d.src_off, d.dst_off, d.len, st, round0 * 32u, a.rounds_per_tile * 32u, lane, nh MODK_RING_ARG);
+        run_tile(a, d.src_off, d.dst_off, d.len, st, round0 * 32u, a.rounds_per_tile * 32u, lane MODK_RING_ARG);
         if ((a.n_tiles - tile) <= stride)
             break;
         tile += stride;
