@@ -16,6 +16,7 @@
 
 #include "../../../include/modulate_b200.h"
 #include "../CArk.h"
+#include "../CDtaFile.h"
 #include "../CEncryptionCycler.h"
 #include "../Error.h"
 #include "../Settings.h"
@@ -175,6 +176,40 @@ eError Decode(std::deque<std::string>&)
     return liWritten == lData.size() ? eError_NoError : eError_FailedToWriteData;
 }
 
+// -dtaset <file> <key> <value>: load a binary DTA file, replace the value that follows the symbol
+// <key> (integer or string, whichever is there) and save it back -- the host-side patch step of a
+// repack.  -dtacopy <in> <out>: load + save (codec round trip).
+eError DtaSet(std::deque<std::string>& laParams)
+{
+    if (laParams.size() < 3)
+        return eError_InvalidParameter;
+    const std::string lFile = laParams[0], lKey = laParams[1], lValue = laParams[2];
+    laParams.erase(laParams.begin(), laParams.begin() + 3);
+    CDtaFile lDta;
+    eError leError = lDta.Load(lFile.c_str());
+    ERROR_RETURN;
+    char* lpEnd = nullptr;
+    const long liValue = std::strtol(lValue.c_str(), &lpEnd, 0);
+    const bool lbNumeric = lpEnd && *lpEnd == 0 && !lValue.empty();
+    if (!((lbNumeric && lDta.SetIntAfter(lKey, (int32_t)liValue)) || lDta.SetStringAfter(lKey, lValue))) {
+        std::cout << "No value of a matching type follows " << lKey << "\n";
+        return eError_InvalidParameter;
+    }
+    return lDta.Save(lFile.c_str());
+}
+
+eError DtaCopy(std::deque<std::string>& laParams)
+{
+    if (laParams.size() < 2)
+        return eError_InvalidParameter;
+    const std::string lIn = laParams[0], lOut = laParams[1];
+    laParams.erase(laParams.begin(), laParams.begin() + 2);
+    CDtaFile lDta;
+    eError leError = lDta.Load(lIn.c_str());
+    ERROR_RETURN;
+    return lDta.Save(lOut.c_str());
+}
+
 void PrintUsage()
 {
     std::cout << "Usage: modulate <options> <command>\n\n"
@@ -189,7 +224,9 @@ void PrintUsage()
               << "  -unpack <out_dir>           Unpack main_<platform>.hdr (+ .ark parts) from the current directory\n"
               << "  -pack <in_dir> <out_dir>    Repack the files the reference header knows\n"
               << "  -pack_add <in_dir> <out_dir> Repack, also adding new files\n"
-              << "  -decode                     Write the deciphered header to main_<platform>.hdr.dec\n";
+              << "  -decode                     Write the deciphered header to main_<platform>.hdr.dec\n"
+              << "  -dtaset <file> <key> <val>  Patch the value following symbol <key> in a binary DTA file\n"
+              << "  -dtacopy <in> <out>         Load and re-save a binary DTA file\n";
 }
 
 }  // namespace
@@ -203,7 +240,7 @@ int main(int argc, char* argv[])
     const sCommandPair kaCommands[] = {
         {"-ps3", PS3},       {"-verbose", EnableVerbose}, {"-force", EnableForceWrite}, {"-packall", EnablePackAll},
         {"-bodykey", BodyKey}, {"-device", Device},       {"-unpack", Unpack},          {"-pack", Pack},
-        {"-pack_add", AddPack}, {"-decode", Decode},
+        {"-pack_add", AddPack}, {"-decode", Decode},   {"-dtaset", DtaSet},          {"-dtacopy", DtaCopy},
     };
 
     std::deque<std::string> laParams;

@@ -60,9 +60,17 @@ def test_repack_on_gpu_end_to_end(tmp_path, ps4):
     key = 0x0BADF00D
     hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), ps4=ps4, n_files=150, n_parts=3, seed=37, body_key=key)
     run(tmp_path, *pre, "-bodykey", str(key), "-unpack", "unpacked")
+    # the host-side patch: one entry is a binary DTA script; change a value in it with the DTB codec
+    from oracle import dta_oracle as do
+    from test_dta_codec import song_config_tree
     victim = next(e for e in hdr.entries if e.size > 100)
-    patched = b"(patched dta)" * 50
-    open(tmp_path / "unpacked" / victim.name, "wb").write(patched)
+    tree = song_config_tree()
+    open(tmp_path / "unpacked" / victim.name, "wb").write(do.serialise([tree]))
+    run(tmp_path, "-dtaset", os.path.join("unpacked", victim.name), "bpm", "174")
+    kids, i = do.find_node(tree, b"bpm")
+    kids[i + 1] = ("int", 0, 174)
+    patched = do.serialise([tree])
+    assert open(tmp_path / "unpacked" / victim.name, "rb").read() == patched
     run(tmp_path, *pre, "-bodykey", str(key), "-packall", "-pack_add", "unpacked", "repacked")
     new, plain = arkfixture.read_header(str(tmp_path / "repacked" / f"main_{plat}.hdr"))
     by_name = {e.name: p for e, p in zip(hdr.entries, payloads)}
