@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if cli_src and (force or stale(CLI)):
         os.makedirs(os.path.dirname(CLI), exist_ok=True)
         cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-               "-o", CLI, *cli_src, "-L", PKG, "-lmodulate_b200", "-Wl,-rpath,$ORIGIN/..", "-ldl", "-lpthread"]
+               "-o", CLI, *cli_src, "-L", PKG, "-lmodulate_b200", "-Wl,-rpath,$ORIGIN/..", "-ldl", "-pthread"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

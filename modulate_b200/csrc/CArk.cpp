@@ -5,7 +5,14 @@
 #include <sys/types.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -15,6 +22,17 @@
 #include "Settings.h"
 
 namespace {
+
+double NowSeconds()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+bool TraceEnabled()
+{
+    const char* lpValue = std::getenv("MOD_TRACE");
+    return lpValue && *lpValue && *lpValue != '0';
+}
 
 bool ReadWholeFile(const std::string& lPath, std::vector<unsigned char>& lOut)
 {
@@ -172,100 +190,313 @@ eError CArk::Load(const char* lpHeaderFilename)
     return eError_NoError;
 }
 
-eError CArk::LoadArkData()
+// Read the parts back to back into the pinned image (reference CArk.cpp:741-755).
+eError CArk::ReadParts()
+{
+    std::vector<FILE*> lFiles(mHeader.maParts.size(), nullptr);
+    const bool lbOk = ReadImageRange(lFiles, 0, muArkDataSize, mpArkData);
+    for (FILE* lpFile : lFiles)
+        if (lpFile)
+            std::fclose(lpFile);
+    return lbOk ? eError_NoError : eError_FailedToOpenFile;
+}
+
+eError CArk::AllocateArkData()
 {
     ReleaseArkData();
     uint64_t luTotalArkSize = 0;
     for (const modark::PartDef& lPart : mHeader.maParts)
         luTotalArkSize += lPart.muSize;
-
     mpArkData = (unsigned char*)mod_host_alloc(luTotalArkSize ? luTotalArkSize : 1);
     if (!mpArkData) {
         std::cout << "Failed to allocate pinned memory for the archive: " << mod_last_error() << "\n";
         return eError_NoData;
     }
     muArkDataSize = luTotalArkSize;
-
-    unsigned char* lpArkPtr = mpArkData;
-    for (const modark::PartDef& lPart : mHeader.maParts) {
-        const std::string lPath = mPartDirectory + lPart.mPath;
-        FILE* lpArkFile = std::fopen(lPath.c_str(), "rb");
-        if (!lpArkFile) {
-            eError leError = eError_FailedToOpenFile;
-            SHOW_ERROR_AND_RETURN;
-        }
-        const size_t liRead = lPart.muSize ? std::fread(lpArkPtr, 1, lPart.muSize, lpArkFile) : 0;
-        std::fclose(lpArkFile);
-        if (liRead != lPart.muSize)
-            std::memset(lpArkPtr + liRead, 0, lPart.muSize - liRead);  // short part: the reference leaves garbage
-        lpArkPtr += lPart.muSize;
-    }
     return eError_NoError;
 }
 
+eError CArk::LoadArkData()
+{
+    eError leError = AllocateArkData();
+    ERROR_RETURN;
+    leError = ReadParts();
+    SHOW_ERROR_AND_RETURN;
+    return eError_NoError;
+}
+
+// Copy bytes [luOffset, luOffset + luSize) of the concatenated part files into lpDst, opening each
+// part on demand (lFiles caches the handles).  Bytes a short part file does not have read as zero.
+bool CArk::ReadImageRange(std::vector<FILE*>& lFiles, uint64_t luOffset, uint64_t luSize, unsigned char* lpDst) const
+{
+    uint64_t luPartStart = 0;
+    for (size_t ii = 0; ii < mHeader.maParts.size() && luSize; ++ii) {
+        const uint64_t luPartSize = mHeader.maParts[ii].muSize;
+        const uint64_t luPartEnd = luPartStart + luPartSize;
+        if (luOffset < luPartEnd) {
+            if (!lFiles[ii]) {
+                lFiles[ii] = std::fopen((mPartDirectory + mHeader.maParts[ii].mPath).c_str(), "rb");
+                if (!lFiles[ii])
+                    return false;
+            }
+            const uint64_t luTake = std::min(luSize, luPartEnd - luOffset);
+            if (fseeko(lFiles[ii], (off_t)(luOffset - luPartStart), SEEK_SET) != 0)
+                return false;
+            const size_t liRead = std::fread(lpDst, 1, (size_t)luTake, lFiles[ii]);
+            if (liRead != luTake)
+                std::memset(lpDst + liRead, 0, (size_t)luTake - liRead);
+            lpDst += luTake;
+            luOffset += luTake;
+            luSize -= luTake;
+        }
+        luPartStart = luPartEnd;
+    }
+    return luSize == 0;
+}
+
+// Extraction is a three-stage host pipeline around the GPU batch, on a small ring of pinned slots
+// instead of the reference's one archive-sized buffer (CArk.cpp:431, :738) and its serial
+// one-file-at-a-time writes (:435-501):
+//   reader thread   the image range a group of entries spans: part files -> the slot's source buffer
+//   this thread     ONE mod_cycle_batch per group (itself an overlapped upload / kernel / download)
+//                   from the slot's source buffer into its byte-packed staging buffer
+//   writer threads  create directories and write the group's files, then hand the slot back
+// so disk reads, PCIe, the kernel and disk writes overlap, and pinned memory is O(slots), not
+// O(archive).
 eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTargetDirectory)
 {
     (void)liFirstFileIndex;  // the reference ignores both and walks the whole table (CArk.cpp:435)
     (void)liNumFiles;
     if (mHeader.maFiles.empty())
         return eError_NoData;
+    const double ldStart = NowSeconds();
 
-    eError leError = LoadArkData();
-    SHOW_ERROR_AND_RETURN;
+    uint64_t luImageSize = 0;
+    for (const modark::PartDef& lPart : mHeader.maParts)
+        luImageSize += lPart.muSize;
 
-    // file table -> device descriptors: gather every entry into a byte-packed staging buffer
+    // validate, then order the entries by where they sit in the image
     const size_t liCount = mHeader.maFiles.size();
-    std::vector<mod_desc> laDescs(liCount);
-    uint64_t luStagingSize = 0;
+    std::vector<uint32_t> laOrder(liCount);
     for (size_t ii = 0; ii < liCount; ++ii) {
         const modark::FileDef& lFile = mHeader.maFiles[ii];
-        if ((uint64_t)lFile.mi64Offset > muArkDataSize || (uint64_t)lFile.miSize > muArkDataSize - (uint64_t)lFile.mi64Offset) {
+        if ((uint64_t)lFile.mi64Offset > luImageSize || (uint64_t)lFile.miSize > luImageSize - (uint64_t)lFile.mi64Offset) {
             std::cout << "Entry " << lFile.mName.c_str() << " lies outside the archive data\n";
-            leError = eError_InvalidData;
+            eError leError = eError_InvalidData;
             SHOW_ERROR_AND_RETURN;
         }
-        laDescs[ii].src_off = (uint64_t)lFile.mi64Offset;
-        laDescs[ii].dst_off = luStagingSize;
-        laDescs[ii].len = (uint32_t)lFile.miSize;
-        laDescs[ii].key = EntryKey(ii);
-        luStagingSize += (uint64_t)lFile.miSize;
+        laOrder[ii] = (uint32_t)ii;
     }
-    unsigned char* lpStaging = (unsigned char*)mod_host_alloc(luStagingSize ? luStagingSize : 1);
-    if (!lpStaging) {
-        std::cout << "Failed to allocate pinned staging memory: " << mod_last_error() << "\n";
-        return eError_NoData;
-    }
-    if (mod_cycle_batch(laDescs.data(), liCount, mpArkData, muArkDataSize, lpStaging, luStagingSize) != MOD_OK) {
-        std::cout << "GPU extract failed: " << mod_last_error() << "\n";
-        mod_host_free(lpStaging);
-        return eError_InvalidData;
+    std::stable_sort(laOrder.begin(), laOrder.end(), [&](uint32_t a, uint32_t b) {
+        return mHeader.maFiles[a].mi64Offset < mHeader.maFiles[b].mi64Offset;
+    });
+
+    // groups of consecutive entries (~32 MiB of payload each) and the image range each one spans
+    struct Group {
+        size_t first, last;           // positions in laOrder
+        uint64_t srcLo, srcHi;        // image range
+        uint64_t payload;
+    };
+    const uint64_t kuGroupBytes = 32ull << 20;
+    std::vector<Group> laGroups;
+    uint64_t luMaxRange = 1, luMaxPayload = 1;
+    for (size_t liFirst = 0; liFirst < liCount;) {
+        Group lGroup{liFirst, liFirst, UINT64_MAX, 0, 0};
+        while (lGroup.last < liCount && (lGroup.payload < kuGroupBytes || lGroup.last == liFirst)) {
+            const modark::FileDef& lFile = mHeader.maFiles[laOrder[lGroup.last]];
+            if (lFile.miSize) {
+                lGroup.srcLo = std::min(lGroup.srcLo, (uint64_t)lFile.mi64Offset);
+                lGroup.srcHi = std::max(lGroup.srcHi, (uint64_t)lFile.mi64Offset + (uint64_t)lFile.miSize);
+            }
+            lGroup.payload += (uint64_t)lFile.miSize;
+            ++lGroup.last;
+        }
+        if (lGroup.srcLo == UINT64_MAX)
+            lGroup.srcLo = lGroup.srcHi = 0;
+        luMaxRange = std::max(luMaxRange, lGroup.srcHi - lGroup.srcLo);
+        luMaxPayload = std::max(luMaxPayload, lGroup.payload);
+        laGroups.push_back(lGroup);
+        liFirst = lGroup.last;
     }
 
-    for (size_t ii = 0; ii < liCount; ++ii) {
-        const modark::FileDef& lFile = mHeader.maFiles[ii];
-        const std::string lOutputPath = std::string(lpTargetDirectory) + lFile.mName;
-        if (KeepExistingOutput(lOutputPath)) {
-            VERBOSE_OUT("Output file already exists, skipping: " << lOutputPath.c_str() << "\n");
-            continue;
+    // the ring of pinned slots
+    constexpr int kiSlots = 3;
+    enum eSlotState { eSlot_Free, eSlot_Filled, eSlot_Busy };
+    struct Slot {
+        unsigned char* mpSource = nullptr;
+        unsigned char* mpStaging = nullptr;
+        eSlotState meState = eSlot_Free;
+    };
+    Slot laSlots[kiSlots];
+    const int liSlotsUsed = (int)std::min<size_t>(kiSlots, laGroups.size());
+    for (int ii = 0; ii < liSlotsUsed; ++ii) {
+        laSlots[ii].mpSource = (unsigned char*)mod_host_alloc(luMaxRange);
+        laSlots[ii].mpStaging = (unsigned char*)mod_host_alloc(luMaxPayload);
+    }
+    auto lFreeSlots = [&]() {
+        for (Slot& lSlot : laSlots) {
+            mod_host_free(lSlot.mpSource);
+            mod_host_free(lSlot.mpStaging);
         }
-        if (!MakeParentDirectories(lOutputPath)) {
-            leError = eError_FailedToCreateDirectory;
-            SHOW_ERROR_AND_RETURN_W(mod_host_free(lpStaging));
-        }
-        VERBOSE_OUT("Writing file " << lOutputPath.c_str() << "\n");
-        FILE* lpOutputFile = std::fopen(lOutputPath.c_str(), "wb");
-        if (!lpOutputFile) {
-            std::cout << "Failed to create " << lOutputPath.c_str() << "\n";  // the reference carries on too (CArk.cpp:488-491)
-            continue;
-        }
-        const size_t liWritten = lFile.miSize ? std::fwrite(lpStaging + laDescs[ii].dst_off, 1, (size_t)lFile.miSize, lpOutputFile) : 0;
-        std::fclose(lpOutputFile);
-        if (liWritten != (size_t)lFile.miSize) {
-            mod_host_free(lpStaging);
-            return eError_FailedToWriteData;
+    };
+    for (int ii = 0; ii < liSlotsUsed; ++ii) {
+        if (!laSlots[ii].mpSource || !laSlots[ii].mpStaging) {
+            std::cout << "Failed to allocate pinned staging memory: " << mod_last_error() << "\n";
+            lFreeSlots();
+            return eError_NoData;
         }
     }
-    mod_host_free(lpStaging);
+    const double ldAllocated = NowSeconds();
+
+    std::mutex lMutex;
+    std::condition_variable lSignal;
+    std::atomic<int> liError{(int)eError_NoError};
+    auto lFail = [&](eError leWhat) {
+        int liExpected = (int)eError_NoError;
+        liError.compare_exchange_strong(liExpected, (int)leWhat);
+        lSignal.notify_all();
+    };
+    auto lWaitFor = [&](Slot& lSlot, eSlotState leWanted) {
+        std::unique_lock<std::mutex> lLock(lMutex);
+        lSignal.wait(lLock, [&]() { return lSlot.meState == leWanted || liError.load() != (int)eError_NoError; });
+        return liError.load() == (int)eError_NoError;
+    };
+    auto lSetState = [&](Slot& lSlot, eSlotState leState) {
+        {
+            std::lock_guard<std::mutex> lLock(lMutex);
+            lSlot.meState = leState;
+        }
+        lSignal.notify_all();
+    };
+
+    // stage 1: reader
+    std::thread lReader([&]() {
+        std::vector<FILE*> lFiles(mHeader.maParts.size(), nullptr);
+        for (size_t gg = 0; gg < laGroups.size(); ++gg) {
+            Slot& lSlot = laSlots[gg % kiSlots];
+            if (!lWaitFor(lSlot, eSlot_Free))
+                break;
+            const Group& lGroup = laGroups[gg];
+            if (!ReadImageRange(lFiles, lGroup.srcLo, lGroup.srcHi - lGroup.srcLo, lSlot.mpSource)) {
+                lFail(eError_FailedToOpenFile);
+                break;
+            }
+            lSetState(lSlot, eSlot_Filled);
+        }
+        for (FILE* lpFile : lFiles)
+            if (lpFile)
+                std::fclose(lpFile);
+    });
+
+    // stage 3: writers
+    struct Job {
+        size_t group;
+        std::vector<uint64_t> offsets;  // staging offset of every entry of the group
+    };
+    std::deque<Job> lJobs;
+    bool lbNoMoreJobs = false;
+    const std::string lTarget = lpTargetDirectory;
+    auto lWriteGroup = [&](const Job& lJob) {
+        const Group& lGroup = laGroups[lJob.group];
+        Slot& lSlot = laSlots[lJob.group % kiSlots];
+        for (size_t ii = lGroup.first; ii < lGroup.last; ++ii) {
+            const modark::FileDef& lFile = mHeader.maFiles[laOrder[ii]];
+            const std::string lOutputPath = lTarget + lFile.mName;
+            if (KeepExistingOutput(lOutputPath)) {
+                VERBOSE_OUT("Output file already exists, skipping: " << lOutputPath.c_str() << "\n");
+                continue;
+            }
+            if (!MakeParentDirectories(lOutputPath)) {
+                lFail(eError_FailedToCreateDirectory);
+                return;
+            }
+            FILE* lpOutputFile = std::fopen(lOutputPath.c_str(), "wb");
+            if (!lpOutputFile) {
+                std::cout << "Failed to create " << lOutputPath.c_str() << "\n";  // the reference carries on too (CArk.cpp:488-491)
+                continue;
+            }
+            const size_t liWritten =
+                lFile.miSize ? std::fwrite(lSlot.mpStaging + lJob.offsets[ii - lGroup.first], 1, (size_t)lFile.miSize, lpOutputFile) : 0;
+            std::fclose(lpOutputFile);
+            if (liWritten != (size_t)lFile.miSize) {
+                lFail(eError_FailedToWriteData);
+                return;
+            }
+        }
+    };
+    auto lWriterLoop = [&]() {
+        for (;;) {
+            Job lJob;
+            {
+                std::unique_lock<std::mutex> lLock(lMutex);
+                lSignal.wait(lLock, [&]() { return !lJobs.empty() || lbNoMoreJobs; });
+                if (lJobs.empty())
+                    return;
+                lJob = std::move(lJobs.front());
+                lJobs.pop_front();
+            }
+            if (liError.load() == (int)eError_NoError)
+                lWriteGroup(lJob);
+            lSetState(laSlots[lJob.group % kiSlots], eSlot_Free);
+        }
+    };
+    std::vector<std::thread> laWriters;
+    for (int ii = 0; ii < 3; ++ii)
+        laWriters.emplace_back(lWriterLoop);
+
+    // stage 2: one GPU batch per group, file table -> device descriptors
+    std::vector<mod_desc> laDescs;
+    for (size_t gg = 0; gg < laGroups.size(); ++gg) {
+        const Group& lGroup = laGroups[gg];
+        Slot& lSlot = laSlots[gg % kiSlots];
+        if (!lWaitFor(lSlot, eSlot_Filled))
+            break;
+        Job lJob;
+        lJob.group = gg;
+        laDescs.clear();
+        uint64_t luOut = 0;
+        for (size_t ii = lGroup.first; ii < lGroup.last; ++ii) {
+            const modark::FileDef& lFile = mHeader.maFiles[laOrder[ii]];
+            mod_desc lDesc;
+            lDesc.src_off = lFile.miSize ? (uint64_t)lFile.mi64Offset - lGroup.srcLo : 0;
+            lDesc.dst_off = luOut;
+            lDesc.len = (uint32_t)lFile.miSize;
+            lDesc.key = EntryKey(laOrder[ii]);
+            laDescs.push_back(lDesc);
+            lJob.offsets.push_back(luOut);
+            luOut += (uint64_t)lFile.miSize;
+        }
+        if (luOut && mod_cycle_batch(laDescs.data(), laDescs.size(), lSlot.mpSource, lGroup.srcHi - lGroup.srcLo,
+                                     lSlot.mpStaging, luOut) != MOD_OK) {
+            std::cout << "GPU extract failed: " << mod_last_error() << "\n";
+            lFail(eError_InvalidData);
+            break;
+        }
+        {
+            std::lock_guard<std::mutex> lLock(lMutex);
+            lSlot.meState = eSlot_Busy;
+            lJobs.push_back(std::move(lJob));
+        }
+        lSignal.notify_all();
+    }
+    {
+        std::lock_guard<std::mutex> lLock(lMutex);
+        lbNoMoreJobs = true;
+    }
+    lSignal.notify_all();
+    const double ldGpuDone = NowSeconds();
+    lReader.join();
+    for (std::thread& lWriter : laWriters)
+        lWriter.join();
+    const double ldWritten = NowSeconds();
+    lFreeSlots();
+    if (TraceEnabled())
+        std::fprintf(stderr, "[mod] ExtractFiles: %zu groups, pinned slots %.3f s, read+GPU %.3f s, writers drain %.3f s, free %.3f s\n",
+                     laGroups.size(), ldAllocated - ldStart, ldGpuDone - ldAllocated, ldWritten - ldGpuDone,
+                     NowSeconds() - ldWritten);
+
+    eError leError = (eError)liError.load();
+    SHOW_ERROR_AND_RETURN;
     return eError_NoError;
 }
 

@@ -5,9 +5,10 @@
 //   Load                  reads the .hdr, deciphers it on the GPU (mod_cycle; reference call site
 //                         CArk.cpp:338-339) and parses it on the host (ArkHeader.cpp)
 //   LoadArkData           concatenates the .ark parts into one PINNED host image (CArk.cpp:723-758)
-//   ExtractFiles          turns the file table into mod_desc descriptors and gathers every entry
-//                         through ONE batched kernel launch (mod_cycle_batch; CArk.cpp:494), then
-//                         writes the files
+//   ExtractFiles          turns the file table into mod_desc descriptors and gathers the entries
+//                         through the batched kernel (mod_cycle_batch; CArk.cpp:494) in a
+//                         reader -> GPU -> writer pipeline over a ring of pinned slots: part files
+//                         are still being read while earlier groups are on the GPU / being written
 //   BuildArk              byte-packs the input files into the image, assigns offsets and part sizes
 //                         (CArk.cpp:760-828) and, when entries carry keys, ciphers them in one batch
 //   SaveArk               serialises + enciphers the header (CArk.cpp:1135-1136) and writes the parts
@@ -18,6 +19,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cstdio>
 #include <string>
 #include <vector>
 
@@ -64,6 +66,9 @@ public:
 
 private:
     int EntryKey(size_t liIndex) const;
+    eError AllocateArkData();
+    eError ReadParts();
+    bool ReadImageRange(std::vector<FILE*>& lFiles, uint64_t luOffset, uint64_t luSize, unsigned char* lpDst) const;
     bool ShouldPackFile(const std::vector<SSongConfig>& laSongs, const char* lpFilename) const;
     void ReleaseArkData();
 

@@ -5,6 +5,8 @@
 //
 // Extensions: -bodykey K (cipher every entry body with key K, stream restarting per entry -- the
 // synthetic per-entry-key configurations), -device N (bind GPU N).
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <deque>
@@ -90,12 +92,19 @@ eError Unpack(std::deque<std::string>& laParams)
     std::cout << lOutputDirectory << "\n";
     WithSlash(lOutputDirectory);
 
+    const bool lbTrace = std::getenv("MOD_TRACE") != nullptr;
+    const auto lNow = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double ldStart = lNow();
     CArk lArkHeader;
     lArkHeader.SetUniformEntryKey(giBodyKey);
     eError leError = lArkHeader.Load(HeaderName().c_str());
     SHOW_ERROR_AND_RETURN;
+    const double ldLoaded = lNow();
     leError = lArkHeader.ExtractFiles(0, lArkHeader.GetNumFiles(), lOutputDirectory.c_str());
     SHOW_ERROR_AND_RETURN;
+    if (lbTrace)
+        std::fprintf(stderr, "[mod] Unpack: Load (CUDA init + header Cycle + parse) %.3f s, ExtractFiles %.3f s\n",
+                     ldLoaded - ldStart, lNow() - ldLoaded);
     return eError_NoError;
 }
 

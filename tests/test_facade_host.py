@@ -28,7 +28,7 @@ def cli():
                                                               os.path.join(ROOT, "tests", "cpp", "mock_abi.cpp")]
     deps = srcs + glob.glob(os.path.join(CSRC, "*.h")) + [os.path.join(ROOT, "include", "modulate_b200.h")]
     if not os.path.exists(MOCK) or any(os.path.getmtime(d) > os.path.getmtime(MOCK) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-o", MOCK,
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", MOCK,
                                *srcs, "-L", os.path.join(ROOT, "oracle"), "-loracle",
                                f"-Wl,-rpath,{os.path.join(ROOT, 'oracle')}"])
     return MOCK
