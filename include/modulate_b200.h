@@ -99,8 +99,8 @@ int32_t mod_key_jump(int32_t key, uint64_t pos);
 
 /* ---- descriptor batches: CArk extract (gather) / build (scatter) / per-entry keys ----------- */
 
-/* Validate `n` host descriptors against the two buffer sizes, upload them, and build the
- * tile -> entry map in HBM.  `dst_align` is (address of dst) & 15 for the buffer the plan will be
+/* Validate `n` host descriptors against the two buffer sizes, upload them, and build the per-tile
+ * records in HBM (the device form of the file table CArk::Load builds, CArk.cpp:401-408).  `dst_align` is (address of dst) & 15 for the buffer the plan will be
  * run on (0 for anything from mod_device_alloc / cudaMalloc).  Entries whose dst ranges overlap
  * give unspecified results (the reference never produces them). */
 int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint64_t dst_bytes,
@@ -109,7 +109,9 @@ int mod_plan_destroy(mod_plan* plan);
 uint64_t mod_plan_payload_bytes(const mod_plan* plan); /* sum of len */
 uint64_t mod_plan_num_tiles(const mod_plan* plan);
 
-/* One launch of the variable-length batched kernel over every descriptor of the plan.
+/* One launch of the variable-length batched kernel over every descriptor of the plan: replaces the
+ * per-entry loops of CArk::ExtractFiles (CArk.cpp:435-501, payload move :494) and CArk::BuildArk
+ * (CArk.cpp:784-822, payload move :807-811), with one CEncryptionCycler::Cycle per entry folded in.
  * Asynchronous on `stream`.  d_src == d_dst with src_off == dst_off is the in-place form. */
 int mod_plan_run(const mod_plan* plan, const void* d_src, void* d_dst, void* stream);
 
@@ -121,7 +123,8 @@ int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t
 
 /* ---- offset-range sharding (host logic, no GPU needed) -------------------------------------- */
 
-/* Byte range [*begin, *end) of a `total`-byte stream owned by `rank` of `world`: equal shares
+/* (No reference counterpart: the reference is single-threaded)
+ * Byte range [*begin, *end) of a `total`-byte stream owned by `rank` of `world`: equal shares
  * rounded to 16-byte boundaries (the last rank takes the remainder). */
 int mod_shard_range(uint64_t total, int rank, int world, uint64_t* begin, uint64_t* end);
 

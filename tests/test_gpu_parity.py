@@ -453,3 +453,27 @@ def test_config4_one_million_small_entries(mb):
         assert not buf.download(o, m).any(), o
     plan.close()
     buf.free()
+
+
+def test_max_length_entry_4gib_minus_1(mb):
+    """One descriptor at the reference's length limit (unsigned int: 2^32 - 1 bytes), destination
+    misaligned by one byte so the entry needs 2^28 + 1 chunks: exercises the top of the tile /
+    jump-table range.  Zero plaintext -> the output is the keystream; windows against the closed form."""
+    n = (1 << 32) - 1
+    key = 0x7FFFFFFE
+    src = DeviceBuffer(n + 16)
+    dst = DeviceBuffer(n + 32)
+    zero = np.zeros(256 << 20, np.uint8)
+    for o in range(0, n + 16, zero.size):
+        src.upload(zero[:min(zero.size, n + 16 - o)], o)
+    guard = np.full(32, 0xAB, np.uint8)
+    dst.upload(guard[:1], 0)
+    dst.upload(guard[:31], n + 1)
+    descs = mb.make_descs([5], [1], [n], [key])
+    mb.cycle_batch(descs, src.ptr, dst.ptr, n + 16, n + 32)
+    for o in (0, 1, 15, 16, 8191, 8192, (1 << 31) - 3, (1 << 31) + 7, n - 8192 - 3, n - 64):
+        w = min(64, n - o)
+        assert (dst.download(1 + o, w) == oracle.cycle_at(np.zeros(w, np.uint8), key, o)).all(), o
+    assert dst.download(0, 1)[0] == 0xAB and (dst.download(n + 1, 31) == 0xAB).all()
+    src.free()
+    dst.free()

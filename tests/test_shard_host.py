@@ -104,8 +104,12 @@ else:
 dist.barrier()
 """)
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    import socket
+    with socket.socket() as sock:  # a free rendezvous port (a fixed one may be taken on a shared box)
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "WORLD2 OK" in out.stdout
