@@ -36,16 +36,31 @@ using modlcg::low8_canonical;
 
 // ---- tuning knobs (defaults chosen from the measurements in profiles/) ------------------------------
 #ifndef MODK_UNROLL
-#define MODK_UNROLL 4            // independent 16-byte chunks in flight per thread
+#define MODK_UNROLL 4            // batched kernel: independent 16-byte chunks in flight per thread
+#endif
+#ifndef MODK_UNROLL_INLINE
+#define MODK_UNROLL_INLINE 2     // contiguous (inline-descriptor) kernel: chunks in flight per thread
 #endif
 #ifndef MODK_CANON_FMA_MASK
 #define MODK_CANON_FMA_MASK 0x5  // which of every 4 bytes canonicalise on the FMA pipe (IMAD.HI) vs ALU (LEA.HI)
 #endif
 #ifndef MODK_MIN_CTAS
-#define MODK_MIN_CTAS 4          // resident CTAs per SM requested through __launch_bounds__ (64 registers)
+#define MODK_MIN_CTAS 3          // batched kernel: resident CTAs per SM requested through __launch_bounds__ (80 registers)
+#endif
+#ifndef MODK_MIN_CTAS_INLINE
+#define MODK_MIN_CTAS_INLINE 4   // contiguous kernel: resident CTAs per SM (64 registers)
+#endif
+#ifndef MODK_INTERLEAVE
+#define MODK_INTERLEAVE 1        // generate the keystream of a whole load group as one basic block (ILP across chunks)
+#endif
+#ifndef MODK_PINGPONG
+#define MODK_PINGPONG 0          // 1: two-stage register software pipeline (next stage's loads before this stage's cipher)
+#endif
+#ifndef MODK_PP_ROUNDS
+#define MODK_PP_ROUNDS 2         // rounds per pipeline stage when MODK_PINGPONG
 #endif
 #ifndef MODK_FULL_GROUPS
-#define MODK_FULL_GROUPS 1       // predicate-free code path for load groups that are interior throughout
+#define MODK_FULL_GROUPS 0       // 1: extra predicate-free code path for fully interior load groups (co-aligned variant); no gain measured
 #endif
 #ifndef MODK_SPECULATE
 #define MODK_SPECULATE 1         // pack low bytes from lazy states, redo the ~1/8000 chunks that needed a canonical subtract
@@ -63,8 +78,7 @@ using modlcg::low8_canonical;
 #define MODK_ST_HINT 0           // 0: st.global   1: st.global.cs (streaming)
 #endif
 
-constexpr int kUnroll = MODK_UNROLL;
-static_assert(kIters % kUnroll == 0, "rounds per tile must be a multiple of the unroll");
+static_assert(kIters % MODK_UNROLL == 0 && kIters % MODK_UNROLL_INLINE == 0, "rounds per tile must be a multiple of the unroll");
 
 // tile index within an entry < 2^32 / kTileBytes + 1; split 10 bits low / rest high
 constexpr int kTw0Size = 1024;
@@ -155,7 +169,12 @@ __device__ __noinline__ uint4 cycle_chunk_rare(uint4 d, uint32_t s, uint32_t two
 // the chunk redone by the exact routine (about one chunk in 8 000).
 __device__ __forceinline__ uint4 cycle_chunk(uint4 d, uint32_t s, const uint32_t two)
 {
-#if MODK_SPECULATE
+#if defined(MODK_EXPERIMENT_COPY_ONLY)
+    // measurement aid (never shipped): no keystream at all -> the memory-system ceiling of this
+    // kernel's access pattern
+    d.x ^= s & two;
+    return d;
+#elif MODK_SPECULATE
     const uint32_t s0 = s;
     uint32_t w[4] = {d.x, d.y, d.z, d.w};
     uint32_t any = 0u;
@@ -287,7 +306,7 @@ __device__ __noinline__ void edge_chunk(const uint8_t* src_entry, uint8_t* dst_e
 // starts kWs words (+ a runtime 0..3 bytes) into its first granule and straddles two.
 // kFull: every chunk of the group is interior, so there are no per-lane predicates and all
 // addresses are one 64-bit pointer per lane plus immediates.
-template <int kWs, bool kFull>
+template <int kWs, bool kFull, int kUnroll>
 __device__ __forceinline__ uint32_t cipher_group(const TileGeom& g, const uint32_t base, const uint32_t m_hi,
                                                  uint32_t v, const uint32_t lane, const uint32_t bs,
                                                  const uint32_t two)
@@ -312,6 +331,53 @@ __device__ __forceinline__ uint32_t cipher_group(const TileGeom& g, const uint32
         }
     }
 
+#if MODK_INTERLEAVE
+    // phase 2a: the kUnroll keystream chunks of the group, generated as ONE basic block so that the
+    // independent 16-step chains interleave (ILP = kUnroll) instead of running one after another;
+    // low bytes are packed straight from the lazy states and the states are OR-ed (see cycle_chunk)
+    uint32_t st[kUnroll];
+    uint32_t v0[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        v0[u] = v;
+        st[u] = v;
+        v = mulmod(v, kRoundJump);  // state just before this lane's chunk of the next round
+    }
+    uint32_t ks[kUnroll][4];
+    uint32_t any = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t b0 = step_lazy(st[u]);
+            const uint32_t b1 = step_lazy(b0);
+            const uint32_t b2 = step_lazy(b1);
+            const uint32_t b3 = step_lazy(b2);
+            st[u] = b3;
+            any |= b0 | b1;
+            any |= b2 | b3;
+            ks[u][j] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+        }
+    }
+    // phase 2b: re-align, apply, store
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        uint4 data = own[u];
+        if (kWs >= 0) {
+            const uint32_t w[8] = {own[u].x, own[u].y, own[u].z, own[u].w, nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
+            constexpr int k = kWs < 0 ? 0 : kWs;
+            data.x = __funnelshift_r(w[k + 0], w[k + 1], bs);
+            data.y = __funnelshift_r(w[k + 1], w[k + 2], bs);
+            data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
+            data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
+        }
+        uint4 out = make_uint4(data.x ^ ks[u][0], data.y ^ ks[u][1], data.z ^ ks[u][2], data.w ^ ks[u][3]);
+        if (__builtin_expect((int32_t)any < 0, 0))  // some state of some chunk needed a canonical subtract: redo exactly
+            out = cycle_chunk_rare(data, v0[u], two);
+        if (fast[u])
+            stg128(dp + 512ull * u, out);
+    }
+#else
     // phase 2: re-align, cipher, store
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -328,10 +394,81 @@ __device__ __forceinline__ uint32_t cipher_group(const TileGeom& g, const uint32
             stg128(dp + 512ull * u, cycle_chunk(data, v, two));
         v = mulmod(v, kRoundJump);  // state just before this lane's chunk of the next round
     }
+#endif
     return v;
 }
 
+// Software-pipelined form (MODK_PINGPONG): two register stages of kPpRounds rounds each; the loads
+// of the next stage are issued BEFORE the current stage is ciphered, so every warp keeps
+// 512 * kPpRounds bytes in flight at all times and a small number of resident warps is enough.
+// (The loop body is the two-stage ping-pong written out so both register sets have static names.)
+constexpr int kPpRounds = MODK_PP_ROUNDS;
+
 template <int kWs>
+struct PpStage {
+    uint4 own[kPpRounds];
+    uint4 nxt[kPpRounds];
+
+    __device__ __forceinline__ void load(const TileGeom& g, uint32_t base, uint32_t lane, uint32_t m_hi)
+    {
+        const uint64_t sp = g.src_al + 16ull * (base + lane);
+#pragma unroll
+        for (int u = 0; u < kPpRounds; ++u) {
+            const uint32_t c = base + (uint32_t)u * 32u + lane;
+            own[u] = make_uint4(0u, 0u, 0u, 0u);
+            nxt[u] = make_uint4(0u, 0u, 0u, 0u);
+            if ((c >= g.f_lo) && (c < m_hi)) {
+                own[u] = ldg128<(kWs < 0)>(sp + 512ull * u);
+                if (kWs >= 0)
+                    nxt[u] = ldg128<false>(sp + 512ull * u + 16ull);
+            }
+        }
+    }
+
+    __device__ __forceinline__ uint32_t finish(const TileGeom& g, uint32_t base, uint32_t lane, uint32_t m_hi,
+                                               uint32_t v, uint32_t bs, uint32_t two) const
+    {
+        const uint64_t dp = g.dst_al + 16ull * (base + lane);
+#pragma unroll
+        for (int u = 0; u < kPpRounds; ++u) {
+            const uint32_t c = base + (uint32_t)u * 32u + lane;
+            uint4 data = own[u];
+            if (kWs >= 0) {
+                const uint32_t w[8] = {own[u].x, own[u].y, own[u].z, own[u].w, nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
+                constexpr int k = kWs < 0 ? 0 : kWs;
+                data.x = __funnelshift_r(w[k + 0], w[k + 1], bs);
+                data.y = __funnelshift_r(w[k + 1], w[k + 2], bs);
+                data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
+                data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
+            }
+            if ((c >= g.f_lo) && (c < m_hi))
+                stg128(dp + 512ull * u, cycle_chunk(data, v, two));
+            v = mulmod(v, kRoundJump);
+        }
+        return v;
+    }
+};
+
+template <int kWs>
+__device__ __forceinline__ void process_interior_pp(const TileGeom& g, uint32_t v, const uint32_t lane,
+                                                    const uint32_t two)
+{
+    const uint32_t bs = (g.shift & 3u) * 8u;
+    const uint32_t m_hi = min(g.c_end, g.f_hi);
+    constexpr uint32_t kStep = 32u * kPpRounds;
+    PpStage<kWs> sa, sb;
+    uint32_t base = g.c_begin;
+    sa.load(g, base, lane, m_hi);
+#pragma unroll 1
+    for (; base < m_hi; base += 2u * kStep) {
+        sb.load(g, base + kStep, lane, m_hi);  // all predicates false past the end of the tile
+        v = sa.finish(g, base, lane, m_hi, v, bs, two);
+        sa.load(g, base + 2u * kStep, lane, m_hi);
+        v = sb.finish(g, base + kStep, lane, m_hi, v, bs, two);
+    }
+}
+
+template <int kWs, int kUnroll>
 __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, const uint32_t lane,
                                                  const uint32_t two)
 {
@@ -342,16 +479,16 @@ __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, 
     uint32_t base = g.c_begin;
     if (MODK_FULL_GROUPS && kWs < 0) {  // co-aligned variant only: four more copies would overflow the I-cache
         if (base < g.f_lo && base < m_hi) {  // the group holding the entry's head edge
-            v = cipher_group<kWs, false>(g, base, m_hi, v, lane, bs, two);
+            v = cipher_group<kWs, false, kUnroll>(g, base, m_hi, v, lane, bs, two);
             base += kGroupChunks;
         }
 #pragma unroll 1
         for (; base + kGroupChunks <= m_hi; base += kGroupChunks)
-            v = cipher_group<kWs, true>(g, base, m_hi, v, lane, bs, two);
+            v = cipher_group<kWs, true, kUnroll>(g, base, m_hi, v, lane, bs, two);
     }
 #pragma unroll 1
     for (; base < m_hi; base += kGroupChunks)
-        v = cipher_group<kWs, false>(g, base, m_hi, v, lane, bs, two);
+        v = cipher_group<kWs, false, kUnroll>(g, base, m_hi, v, lane, bs, two);
 }
 
 #if MODK_BULK
@@ -443,9 +580,14 @@ __device__ __forceinline__ uint32_t tile_start_state(int32_t key, uint32_t h0, u
 #else
 #define MODK_RING_PARAM
 #define MODK_RING_ARG
-#define MODK_INTERIOR(K) process_interior<K>(g, v, lane, a.two)
+#if MODK_PINGPONG
+#define MODK_INTERIOR(K) process_interior_pp<K>(g, v, lane, a.two)
+#else
+#define MODK_INTERIOR(K) process_interior<K, kUnroll>(g, v, lane, a.two)
+#endif
 #endif
 
+template <int kUnroll>
 __device__ __forceinline__ void run_tile(const BatchArgs& a, const uint64_t src_off, const uint64_t dst_off,
                                          const uint32_t len, const uint32_t st, const uint32_t c_begin,
                                          const uint32_t tile_chunks, const uint32_t lane MODK_RING_PARAM)
@@ -556,7 +698,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_ker
         TileRec nxt = cur;
         if (more)
             nxt = load_tile_rec(a.tiles + tile + stride);
-        run_tile(a, cur.src_off, cur.dst_off, cur.len, cur.state, cur.tin * (uint32_t)kChunksPerTile,
+        run_tile<MODK_UNROLL>(a, cur.src_off, cur.dst_off, cur.len, cur.state, cur.tin * (uint32_t)kChunksPerTile,
                  (uint32_t)kChunksPerTile, lane MODK_RING_ARG);
         if (!more)
             break;
@@ -568,7 +710,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_ker
 // Same kernel with the (few) descriptors in the parameter block: nothing to upload, nothing to
 // allocate, so a contiguous Cycle() is a single asynchronous launch.  The per-tile state comes
 // from the constant-bank jump tables instead of a tile record.
-__global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS)
+__global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS_INLINE)
 cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
 {
     MODK_RING_SETUP
@@ -583,7 +725,7 @@ cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
         const uint32_t h0 = (uint32_t)((uint64_t)a.dst + d.dst_off) & 15u;
         const uint32_t st = mulmod(tile_start_state(d.key, h0, round0 / (uint32_t)kIters),
                                    c_round_pow[round0 % (uint32_t)kIters]);
-        run_tile(a, d.src_off, d.dst_off, d.len, st, round0 * 32u, a.rounds_per_tile * 32u, lane MODK_RING_ARG);
+        run_tile<MODK_UNROLL_INLINE>(a, d.src_off, d.dst_off, d.len, st, round0 * 32u, a.rounds_per_tile * 32u, lane MODK_RING_ARG);
         if ((a.n_tiles - tile) <= stride)
             break;
         tile += stride;
@@ -646,31 +788,33 @@ cudaError_t upload_tables()
     return cudaSuccess;
 }
 
-cudaError_t persistent_grid(int* grid_out)
+cudaError_t persistent_grid(int* grid_out, bool inline_kernel)
 {
-    static int cached[64] = {};
+    static int cached[2][64] = {};
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess)
         return err;
     if (dev < 0 || dev >= 64)
         return cudaErrorInvalidDevice;
-    if (cached[dev] == 0) {
-        int sms = 0, per_sm_a = 0, per_sm_b = 0;
+    int& slot = cached[inline_kernel ? 1 : 0][dev];
+    if (slot == 0) {
+        int sms = 0, per_sm = 0;
         if ((err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return err;
-        if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, cycle_batch_kernel, kThreadsPerCta, 0)) != cudaSuccess) return err;
-        if ((err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, cycle_inline_kernel, kThreadsPerCta, 0)) != cudaSuccess) return err;
-        const int per_sm = per_sm_a < per_sm_b ? per_sm_a : per_sm_b;
-        cached[dev] = sms * (per_sm > 0 ? per_sm : 1);
+        err = inline_kernel ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cycle_inline_kernel, kThreadsPerCta, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cycle_batch_kernel, kThreadsPerCta, 0);
+        if (err != cudaSuccess)
+            return err;
+        slot = sms * (per_sm > 0 ? per_sm : 1);
     }
-    *grid_out = cached[dev];
+    *grid_out = slot;
     return cudaSuccess;
 }
 
-static cudaError_t grid_for_tiles(uint32_t n_tiles, unsigned* grid)
+static cudaError_t grid_for_tiles(uint32_t n_tiles, unsigned* grid, bool inline_kernel)
 {
     int cap = 0;
-    cudaError_t err = persistent_grid(&cap);
+    cudaError_t err = persistent_grid(&cap, inline_kernel);
     if (err != cudaSuccess)
         return err;
     const unsigned want = (unsigned)((n_tiles + (uint32_t)kWarpsPerCta - 1u) / (uint32_t)kWarpsPerCta);
@@ -683,7 +827,7 @@ cudaError_t launch_batch(const BatchArgs& args, cudaStream_t stream)
     if (args.n_tiles == 0)
         return cudaSuccess;
     unsigned grid = 0;
-    cudaError_t err = grid_for_tiles(args.n_tiles, &grid);
+    cudaError_t err = grid_for_tiles(args.n_tiles, &grid, false);
     if (err != cudaSuccess)
         return err;
     cycle_batch_kernel<<<grid, kThreadsPerCta, 0, stream>>>(args);
@@ -695,7 +839,7 @@ cudaError_t launch_batch_inline(const BatchArgs& args, const InlineDescs& descs,
     if (args.n_tiles == 0)
         return cudaSuccess;
     unsigned grid = 0;
-    cudaError_t err = grid_for_tiles(args.n_tiles, &grid);
+    cudaError_t err = grid_for_tiles(args.n_tiles, &grid, true);
     if (err != cudaSuccess)
         return err;
     cycle_inline_kernel<<<grid, kThreadsPerCta, 0, stream>>>(args, descs);

@@ -71,7 +71,7 @@ __host__ __device__ inline uint32_t tiles_for_entry(uint32_t h0, uint32_t len,
 
 cudaError_t upload_tables();  // jump tables -> __constant__ / global memory of the current device
 // Persistent grid size for the current device (SM count x resident CTAs per SM), cached per device.
-cudaError_t persistent_grid(int* grid_out);
+cudaError_t persistent_grid(int* grid_out, bool inline_kernel);
 cudaError_t launch_batch(const BatchArgs& args, cudaStream_t stream);
 cudaError_t launch_batch_inline(const BatchArgs& args, const InlineDescs& descs, cudaStream_t stream);
 // Plan kernel: expands descriptors into per-tile records (binary search + jump-ahead per tile).

@@ -200,7 +200,7 @@ int launch_contiguous(const uint8_t* d_src, uint8_t* d_dst, uint64_t len, int32_
     uint32_t rounds = (uint32_t)modk::kIters;
     {
         int grid_cap = 0;
-        CUDA_TRY(modk::persistent_grid(&grid_cap));
+        CUDA_TRY(modk::persistent_grid(&grid_cap, true));
         const uint64_t want_tiles = (uint64_t)grid_cap * modk::kWarpsPerCta;
         while (rounds > 1 && (len + 512ull * rounds - 1) / (512ull * rounds) < want_tiles)
             rounds >>= 1;
