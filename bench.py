@@ -247,6 +247,16 @@ def run_gpu_arm(args) -> None:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    # NUMA placement: run this rank (and first-touch its pinned buffers) on the CPUs closest to its GPU
+    all_cpus = os.sched_getaffinity(0)
+    numa_pinned = False
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        numa_pinned = os.sched_getaffinity(0) != all_cpus
+    except Exception:
+        pass
     mb.init(local)
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream()
@@ -400,6 +410,7 @@ def run_gpu_arm(args) -> None:
     #    byte-for-byte check of the GPU output of those entries against it
     cpu = None
     if world == 1:
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core
         setup = cpu_reference_setup(gdescs, target_seconds=2.0)
         work = np.empty_like(setup["plain"])
         cpu_reference_step(setup, work)
@@ -426,7 +437,8 @@ def run_gpu_arm(args) -> None:
                    "layout": "byte-packed source entries, 16-byte-aligned extract slots, per-entry keys, "
                              "HDR Cycle + one batched launch per step",
                    "l2": "inputs (1 GiB read + 1 GiB written per step) exceed the 126 MB L2; no flush needed",
-                   "sharding": "mod_shard_descs offset ranges, no collective" if world > 1 else "single GPU"},
+                   "sharding": "mod_shard_descs offset ranges, no collective" if world > 1 else "single GPU",
+                   "host": "rank pinned to its GPU's NUMA-local CPUs (NVML affinity)" if numa_pinned else "default CPU affinity"},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "api": "mod_cycle + mod_cycle_batch on pinned host buffers"},
