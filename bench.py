@@ -210,7 +210,7 @@ def run_reference_arm(args) -> None:
     gbs = setup["bytes"] * args.steps / t / 1e9
     sample = f"first {setup['n']} entries ({setup['bytes']} payload bytes) of the {args.workload} archive per step"
     line = {
-        "impl": "reference", "metric": "ark_decrypt_throughput", "value": gbs, "unit": "GB/s",
+        "impl": "reference", "metric": "ark_dtb_decrypt_throughput", "value": gbs, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": args.workload, "entries": int(len(descs)), "sample": sample},
@@ -430,7 +430,7 @@ def run_gpu_arm(args) -> None:
                "gpu_bytes_checked_against_it": checked}
 
     line = {
-        "metric": "ark_decrypt_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "metric": "ark_dtb_decrypt_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": args.workload, "entries_per_gpu": int(len(descs)), "payload_bytes_per_gpu": payload,

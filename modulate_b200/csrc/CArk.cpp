@@ -602,11 +602,13 @@ eError CArk::BuildArk(const char* lpInputDirectory, std::vector<SSongConfig> laS
     }
     muArkDataSize = luTotalArkSize;
 
+    // pass 1 (serial, sizes only): byte-packed running offsets and part sizes
     std::string lRoot = lpInputDirectory;
     size_t liArkIndex = 0;
     int64_t li64Allowed = mHeader.maParts[0].muSize;
     uint64_t luPtr = 0, luPartStart = 0;
     std::vector<mod_desc> laDescs;
+    std::vector<size_t> laToRead;
     bool lbAnyKey = false;
     for (size_t ii = 0; ii < mHeader.maFiles.size(); ++ii) {
         modark::FileDef& lFile = mHeader.maFiles[ii];
@@ -614,18 +616,9 @@ eError CArk::BuildArk(const char* lpInputDirectory, std::vector<SSongConfig> laS
             lFile.mi64Offset = 0;
             continue;
         }
-        const std::string lFilename = lRoot + lFile.mName;
-        FILE* lpInputFile = std::fopen(lFilename.c_str(), "rb");
-        if (!lpInputFile) {
-            eError leError = eError_FailedToOpenFile;
-            SHOW_ERROR_AND_RETURN;
-        }
         // scatter: the file lands at the running, byte-packed offset
         lFile.mi64Offset = (int64_t)luPtr;
-        const size_t liRead = std::fread(mpArkData + luPtr, 1, (size_t)lFile.miSize, lpInputFile);
-        std::fclose(lpInputFile);
-        if (liRead != (size_t)lFile.miSize)
-            std::memset(mpArkData + luPtr + liRead, 0, (size_t)lFile.miSize - liRead);
+        laToRead.push_back(ii);
         const int liKey = EntryKey(ii);
         lbAnyKey = lbAnyKey || (liKey % 0x7FFFFFFF) != 0;
         laDescs.push_back(mod_desc{luPtr, luPtr, (uint32_t)lFile.miSize, liKey});
@@ -648,6 +641,41 @@ eError CArk::BuildArk(const char* lpInputDirectory, std::vector<SSongConfig> laS
         }
     }
     mHeader.maParts[liArkIndex].muSize = (unsigned int)(luPtr - luPartStart);
+
+    // pass 2: the payload reads (the reference's one fread per file, CArk.cpp:796-811) fanned out over
+    // a few threads -- thousands of small files are latency-bound on any real file system
+    std::atomic<size_t> liNext{0};
+    std::atomic<bool> lbOpenFailed{false};
+    auto lReadFiles = [&]() {
+        for (;;) {
+            const size_t liSlot = liNext.fetch_add(1);
+            if (liSlot >= laToRead.size() || lbOpenFailed.load())
+                return;
+            const modark::FileDef& lFile = mHeader.maFiles[laToRead[liSlot]];
+            FILE* lpInputFile = std::fopen((lRoot + lFile.mName).c_str(), "rb");
+            if (!lpInputFile) {
+                lbOpenFailed.store(true);
+                return;
+            }
+            unsigned char* lpDst = mpArkData + lFile.mi64Offset;
+            const size_t liRead = std::fread(lpDst, 1, (size_t)lFile.miSize, lpInputFile);
+            std::fclose(lpInputFile);
+            if (liRead != (size_t)lFile.miSize)
+                std::memset(lpDst + liRead, 0, (size_t)lFile.miSize - liRead);
+        }
+    };
+    {
+        std::vector<std::thread> laReaders;
+        for (int ii = 0; ii < 3; ++ii)
+            laReaders.emplace_back(lReadFiles);
+        lReadFiles();
+        for (std::thread& lThread : laReaders)
+            lThread.join();
+    }
+    if (lbOpenFailed.load()) {
+        eError leError = eError_FailedToOpenFile;
+        SHOW_ERROR_AND_RETURN;
+    }
 
     // entries that carry a key are ciphered where they lie, all in one batched launch
     if (lbAnyKey && !laDescs.empty()) {
