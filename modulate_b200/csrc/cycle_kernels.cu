@@ -69,7 +69,7 @@ using modlcg::low8_canonical;
 #define MODK_BULK 0              // 1: stage the source through a per-warp shared-memory ring filled by bulk-async copies (TMA 1-D)
 #endif
 #ifndef MODK_STAGES
-#define MODK_STAGES 8            // ring depth per warp (rounds of 512 B in flight) when MODK_BULK
+#define MODK_STAGES 2            // ring depth per warp (load groups in flight) when MODK_BULK
 #endif
 #ifndef MODK_LD_HINT
 #define MODK_LD_HINT 0           // 0: ld.global   1: .L1::no_allocate on the co-aligned path   2: .cs everywhere
@@ -209,7 +209,7 @@ __device__ __forceinline__ uint4 keystream_chunk(uint32_t s, const uint32_t two)
 #if MODK_BULK
 // ---- bulk-async staging: mbarrier + cp.async.bulk (SASS: UBLKCP / SYNCS) --------------------------------
 constexpr int kStages = MODK_STAGES;
-constexpr uint32_t kStageBytes = 512u + 16u;  // 32 granules + the one the last lane straddles into
+constexpr uint32_t kStageBytes = 16u * (32u * (MODK_UNROLL > MODK_UNROLL_INLINE ? MODK_UNROLL : MODK_UNROLL_INLINE) + 1u);  // one load group + the straddled granule
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -306,10 +306,18 @@ __device__ __noinline__ void edge_chunk(const uint8_t* src_entry, uint8_t* dst_e
 // starts kWs words (+ a runtime 0..3 bytes) into its first granule and straddles two.
 // kFull: every chunk of the group is interior, so there are no per-lane predicates and all
 // addresses are one 64-bit pointer per lane plus immediates.
-template <int kWs, bool kFull, int kUnroll>
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+
+// kSmem: the group's source granules were staged in shared memory at `stage` (granule j of the
+// group at stage + 16 j) by a bulk-async copy; `after_loads` runs once the data is in registers
+// (the bulk path refills the stage there, before the integer work starts).
+template <int kWs, bool kFull, int kUnroll, bool kSmem = false, typename AfterLoads = NoHook>
 __device__ __forceinline__ uint32_t cipher_group(const TileGeom& g, const uint32_t base, const uint32_t m_hi,
                                                  uint32_t v, const uint32_t lane, const uint32_t bs,
-                                                 const uint32_t two)
+                                                 const uint32_t two, const uint32_t stage = 0u,
+                                                 AfterLoads after_loads = AfterLoads())
 {
     uint4 own[kUnroll];
     uint4 nxt[kUnroll];
@@ -325,11 +333,21 @@ __device__ __forceinline__ uint32_t cipher_group(const TileGeom& g, const uint32
         own[u] = make_uint4(0u, 0u, 0u, 0u);
         nxt[u] = make_uint4(0u, 0u, 0u, 0u);
         if (fast[u]) {
-            own[u] = ldg128<(kWs < 0)>(sp + 512ull * u);
-            if (kWs >= 0)
-                nxt[u] = ldg128<false>(sp + 512ull * u + 16ull);
+#if MODK_BULK
+            if (kSmem) {
+                own[u] = lds128(stage + 16u * (32u * (uint32_t)u + lane));
+                if (kWs >= 0)
+                    nxt[u] = lds128(stage + 16u * (32u * (uint32_t)u + lane) + 16u);
+            } else
+#endif
+            {
+                own[u] = ldg128<(kWs < 0)>(sp + 512ull * u);
+                if (kWs >= 0)
+                    nxt[u] = ldg128<false>(sp + 512ull * u + 16ull);
+            }
         }
     }
+    after_loads();
 
 #if MODK_INTERLEAVE
     // phase 2a: the kUnroll keystream chunks of the group, generated as ONE basic block so that the
@@ -492,12 +510,13 @@ __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, 
 }
 
 #if MODK_BULK
-// Interior chunks through the shared-memory ring: lane 0 keeps up to kStages rounds (512 B each, +16
-// when the chunk straddles two granules) in flight with bulk-async copies; per round the warp first
-// computes its 16 keystream bytes (no memory dependence), then waits for the stage, reads its
-// granule(s) with LDS.128, funnel-shifts, XORs and stores, and finally hands the stage back to be
-// refilled kStages rounds ahead.  Loads in flight cost shared memory, not registers.
-template <int kWs>
+// Interior chunks through a per-warp shared-memory ring (MODK_BULK): lane 0 keeps kStages load
+// groups (kUnroll rounds = 512 * kUnroll bytes each, +16 when chunks straddle two granules) in flight
+// with ONE bulk-async copy per group; per group the warp waits for its stage, pulls it into
+// registers with LDS.128, hands the stage straight back to be refilled kStages groups ahead, and
+// only then runs the (interleaved) integer work and the stores.  Loads in flight cost shared
+// memory instead of registers, and their number is fixed by the ring, not by the warp count.
+template <int kWs, int kUnroll>
 __device__ __forceinline__ void process_interior_bulk(const TileGeom& g, uint32_t v, const uint32_t lane,
                                                       const uint32_t two, WarpRing& ring)
 {
@@ -506,12 +525,13 @@ __device__ __forceinline__ void process_interior_bulk(const TileGeom& g, uint32_
     const uint32_t lo = max(g.c_begin, g.f_lo);
     if (lo >= m_hi)
         return;
-    const uint32_t n_rounds = (m_hi - g.c_begin + 31u) >> 5;
+    constexpr uint32_t kGroupChunks = 32u * kUnroll;
     constexpr uint32_t kExtra = (kWs >= 0) ? 1u : 0u;
+    const uint32_t n_groups = (m_hi - g.c_begin + kGroupChunks - 1u) / kGroupChunks;
 
-    auto issue = [&](uint32_t r, uint32_t stage) {
-        const uint32_t base = g.c_begin + 32u * r;
-        const uint32_t a = max(base, lo), b = min(base + 32u, m_hi);
+    auto issue = [&](uint32_t gi, uint32_t stage) {
+        const uint32_t base = g.c_begin + kGroupChunks * gi;
+        const uint32_t a = max(base, lo), b = min(base + kGroupChunks, m_hi);
         if (lane == 0 && b > a) {
             const uint32_t bytes = 16u * (b - a + kExtra);
             const uint32_t bar = ring.bars + 8u * stage;
@@ -521,46 +541,27 @@ __device__ __forceinline__ void process_interior_bulk(const TileGeom& g, uint32_
     };
 
     const uint32_t first_slot = ring.slot;
-    const uint32_t pre = min(n_rounds, (uint32_t)kStages);
-    for (uint32_t r = 0; r < pre; ++r)
-        issue(r, (first_slot + r) % (uint32_t)kStages);
+    const uint32_t pre = min(n_groups, (uint32_t)kStages);
+    for (uint32_t gi = 0; gi < pre; ++gi)
+        issue(gi, (first_slot + gi) % (uint32_t)kStages);
 
 #pragma unroll 1
-    for (uint32_t r = 0; r < n_rounds; ++r) {
-        const uint32_t stage = (first_slot + r) % (uint32_t)kStages;
-        const uint32_t base = g.c_begin + 32u * r;
-        const uint32_t c = base + lane;
-        const bool fast = (c >= lo) && (c < m_hi);
-        const bool any = max(base, lo) < min(base + 32u, m_hi);  // warp-uniform: this round fetched something
-        const uint4 ks = keystream_chunk(v, two);
-        if (any) {
+    for (uint32_t gi = 0; gi < n_groups; ++gi) {
+        const uint32_t stage = (first_slot + gi) % (uint32_t)kStages;
+        const uint32_t base = g.c_begin + kGroupChunks * gi;
+        if (max(base, lo) < min(base + kGroupChunks, m_hi)) {  // warp-uniform: this group fetched something
             mbar_wait(ring.bars + 8u * stage, (ring.phases >> stage) & 1u);
             ring.phases ^= 1u << stage;
         }
-        if (fast) {
-            const uint32_t at = ring.data + stage * kStageBytes + 16u * lane;
-            uint4 data = lds128(at);
-            if (kWs >= 0) {
-                const uint4 nx = lds128(at + 16u);
-                const uint32_t w[8] = {data.x, data.y, data.z, data.w, nx.x, nx.y, nx.z, nx.w};
-                constexpr int k = kWs < 0 ? 0 : kWs;
-                data.x = __funnelshift_r(w[k + 0], w[k + 1], bs);
-                data.y = __funnelshift_r(w[k + 1], w[k + 2], bs);
-                data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
-                data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
-            }
-            data.x ^= ks.x;
-            data.y ^= ks.y;
-            data.z ^= ks.z;
-            data.w ^= ks.w;
-            stg128(g.dst_al + 16ull * c, data);
-        }
-        __syncwarp();  // every lane has consumed the stage (its LDS results fed the XOR above)
-        if (r + (uint32_t)kStages < n_rounds)
-            issue(r + (uint32_t)kStages, stage);
-        v = mulmod(v, kRoundJump);
+        auto refill = [&]() {
+            __syncwarp();  // every lane holds its granules in registers: the stage may be overwritten
+            if (gi + (uint32_t)kStages < n_groups)
+                issue(gi + (uint32_t)kStages, stage);
+        };
+        v = cipher_group<kWs, false, kUnroll, true>(g, base, m_hi, v, lane, bs, two,
+                                                    ring.data + stage * kStageBytes, refill);
     }
-    ring.slot = (first_slot + n_rounds) % (uint32_t)kStages;
+    ring.slot = (first_slot + n_groups) % (uint32_t)kStages;
 }
 #endif
 
@@ -576,7 +577,7 @@ __device__ __forceinline__ uint32_t tile_start_state(int32_t key, uint32_t h0, u
 #if MODK_BULK
 #define MODK_RING_PARAM , WarpRing& ring
 #define MODK_RING_ARG , ring
-#define MODK_INTERIOR(K) process_interior_bulk<K>(g, v, lane, a.two, ring)
+#define MODK_INTERIOR(K) process_interior_bulk<K, kUnroll>(g, v, lane, a.two, ring)
 #else
 #define MODK_RING_PARAM
 #define MODK_RING_ARG
