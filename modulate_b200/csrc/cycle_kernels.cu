@@ -28,6 +28,8 @@
 #include "cycle_kernels.cuh"
 #include "lcg.h"
 
+#include <cstdlib>
+
 namespace modk {
 
 using modlcg::mulmod;
@@ -49,6 +51,9 @@ using modlcg::low8_canonical;
 #endif
 #ifndef MODK_MIN_CTAS_INLINE
 #define MODK_MIN_CTAS_INLINE 4   // contiguous kernel: resident CTAs per SM (64 registers)
+#endif
+#ifndef MODK_GRID_MODE
+#define MODK_GRID_MODE 0         // 0: persistent grid (SMs x resident CTAs), 1: one tile per warp, CTAs retire
 #endif
 #ifndef MODK_INTERLEAVE
 #define MODK_INTERLEAVE 1        // generate the keystream of a whole load group as one basic block (ILP across chunks)
@@ -819,7 +824,11 @@ static cudaError_t grid_for_tiles(uint32_t n_tiles, unsigned* grid, bool inline_
     if (err != cudaSuccess)
         return err;
     const unsigned want = (unsigned)((n_tiles + (uint32_t)kWarpsPerCta - 1u) / (uint32_t)kWarpsPerCta);
-    *grid = want < (unsigned)cap ? want : (unsigned)cap;
+    static const int mode = []() {
+        const char* v = getenv("MOD_GRID_MODE");  // tuning aid: 1 = one tile per warp, CTAs retire (non-persistent)
+        return v ? atoi(v) : MODK_GRID_MODE;
+    }();
+    *grid = (mode == 1 || want < (unsigned)cap) ? want : (unsigned)cap;
     return cudaSuccess;
 }
 
