@@ -23,7 +23,10 @@
 
 namespace {
 
-constexpr int kPipeSlots = 4;               // slices in flight on the host-pointer path
+#ifndef MOD_PIPE_SLOTS
+#define MOD_PIPE_SLOTS 4
+#endif
+constexpr int kPipeSlots = MOD_PIPE_SLOTS;               // slices in flight on the host-pointer path
 constexpr uint64_t kMaxPiece = 1ull << 30;  // a contiguous stream is cut into <= 1 GiB pieces
 constexpr int kMaxDevices = 64;
 
