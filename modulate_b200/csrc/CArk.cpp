@@ -76,6 +76,21 @@ bool MakeParentDirectories(const std::string& lFilePath)
     return true;
 }
 
+// An entry name may not climb out of the target directory ("..": the reference would follow it).
+bool EscapesTarget(const std::string& lName)
+{
+    size_t liStart = 0;
+    for (;;) {
+        const size_t liSlash = lName.find('/', liStart);
+        const std::string lPart = lName.substr(liStart, liSlash == std::string::npos ? std::string::npos : liSlash - liStart);
+        if (lPart == "..")
+            return true;
+        if (liSlash == std::string::npos)
+            return false;
+        liStart = liSlash + 1;
+    }
+}
+
 // Existing non-empty output is kept only when overwriting is disabled (reference CArk.cpp:439-454).
 bool KeepExistingOutput(const std::string& lPath)
 {
@@ -402,6 +417,10 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
         for (size_t ii = lGroup.first; ii < lGroup.last; ++ii) {
             const modark::FileDef& lFile = mHeader.maFiles[laOrder[ii]];
             const std::string lOutputPath = lTarget + lFile.mName;
+            if (EscapesTarget(lFile.mName)) {
+                std::cout << "Refusing to write outside the target directory: " << lFile.mName.c_str() << "\n";
+                continue;
+            }
             if (KeepExistingOutput(lOutputPath)) {
                 VERBOSE_OUT("Output file already exists, skipping: " << lOutputPath.c_str() << "\n");
                 continue;

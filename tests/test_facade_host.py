@@ -190,3 +190,31 @@ def test_header_codec_roundtrip_python_side():
                 assert ao.file_hash(back.entries[idx].name, n) == b
                 idx = back.entries[idx].flags1
         assert reached == set(range(n))
+
+
+def test_header_fuzz_never_crashes(cli, tmp_path):
+    """Random corruptions of a valid (deciphered-then-reciphered) header: the loader must answer
+    with an eError or succeed, never crash or hang (the reference reads out of bounds here)."""
+    hdr, _, plain = arkfixture.write_archive(str(tmp_path), n_files=40, n_parts=2, seed=17)
+    path = tmp_path / "main_ps4.hdr"
+    rng = np.random.default_rng(99)
+    crashes = []
+    for trial in range(120):
+        bad = bytearray(plain)
+        kind = trial % 4
+        if kind == 0:      # flip a few random bytes after the magic
+            for _ in range(int(rng.integers(1, 6))):
+                bad[int(rng.integers(4, len(bad)))] = int(rng.integers(0, 256))
+        elif kind == 1:    # overwrite a random aligned word with an extreme value
+            pos = int(rng.integers(1, len(bad) // 4)) * 4
+            bad[pos:pos + 4] = int(rng.choice([0x7FFFFFFF, 0xFFFFFFFF, 0x80000000, 25001, 101])).to_bytes(4, "little")
+        elif kind == 2:    # truncate
+            bad = bad[:int(rng.integers(4, len(bad)))]
+        else:              # append garbage
+            bad += bytes(int(x) for x in rng.integers(0, 256, size=int(rng.integers(1, 64))))
+        enc = bytes(bad[:4]) + oracle.cycle(np.frombuffer(bytes(bad[4:]), np.uint8), ao.KEY_PS4).tobytes()
+        path.write_bytes(enc)
+        out = subprocess.run([cli, "-unpack", f"o{trial}"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+        if out.returncode not in (0, 255):
+            crashes.append((trial, kind, out.returncode))
+    assert not crashes, crashes
