@@ -70,7 +70,17 @@ def aligned_slots(sizes: np.ndarray) -> np.ndarray:
     return synth.packed_offsets(padded)
 
 
+def cfg3_descs(mb):
+    """16 GiB multi-part set: 32 parts x 512 MiB (kuMaxArkSize, reference CArk.cpp:19), one
+    (offset, len, key) per part, ciphered in place (BASELINE configs[2])."""
+    part = 512 << 20
+    off = np.arange(32, dtype=np.int64) * part
+    return mb.make_descs(off, off, np.full(32, part, np.int64), synth.entry_keys(32, seed=synth.SEED + 3))
+
+
 def build_global_descs(mb, workload: str, world: int):
+    if workload == "cfg3":
+        return cfg3_descs(mb)
     offs, sizes, keys = [], [], []
     for part in range(world):
         o, s, k = cfg2_entries(part) if workload == "cfg2" else cfg4_entries(part)
@@ -151,7 +161,11 @@ class ClockSampler:
 
 # ---- CPU arm: the unmodified reference cipher on the host cores ------------------------------------
 
-def cpu_reference_setup(descs: np.ndarray, target_seconds: float = 1.5):
+def zeros_payload(offset: int, n: int) -> np.ndarray:
+    return np.zeros(n, dtype=np.uint8)
+
+
+def cpu_reference_setup(descs: np.ndarray, target_seconds: float = 1.5, payload_fn=None):
     """Pick a bounded sample (whole entries from the front of the table) that the reference cipher,
     fanned out over all host threads, finishes in about `target_seconds`."""
     import oracle
@@ -167,11 +181,11 @@ def cpu_reference_setup(descs: np.ndarray, target_seconds: float = 1.5):
     budget = rate1 * cores * target_seconds
     csum = np.cumsum(descs["len"].astype(np.int64))
     n = int(np.searchsorted(csum, budget, side="right"))
-    n = max(min(n, len(descs)), min(len(descs), 4 * cores))
+    n = max(min(n, len(descs)), min(len(descs), 4 * cores if int(descs["len"].max()) < (64 << 20) else 1))
     sample = descs[:n]
     lo = int(sample["src_off"].min())
     hi = int((sample["src_off"] + sample["len"]).max())
-    plain = synth.payload(lo, hi - lo)
+    plain = (payload_fn or synth.payload)(lo, hi - lo)
     parts = np.zeros(n, dtype=oracle.PART_DTYPE)
     parts["off"] = sample["src_off"] - lo
     parts["len"] = sample["len"]
@@ -200,7 +214,7 @@ def run_reference_arm(args) -> None:
         return
     import modulate_b200 as mb  # host-only use: make_descs (no GPU work on this arm)
     descs = build_global_descs(mb, args.workload, 1)
-    setup = cpu_reference_setup(descs, target_seconds=1.5)
+    setup = cpu_reference_setup(descs, target_seconds=1.5, payload_fn=zeros_payload if args.workload == "cfg3" else None)
     work = np.empty_like(setup["plain"])
     for _ in range(args.warmup):
         cpu_reference_step(setup, work)
@@ -269,12 +283,18 @@ def run_gpu_arm(args) -> None:
     payload = int(descs["len"].sum())
 
     # -- inputs resident in HBM: the shard's slice of the set image, and the encrypted HDR
-    d_src = torch.empty(src_bytes, dtype=torch.uint8, device=dev)
+    in_place = args.workload == "cfg3"  # the multi-part set is ciphered where it lies; all-zero payload
+    payload_fn = zeros_payload if in_place else synth.payload
     step_bytes = 64 << 20
-    for o in range(0, src_bytes, step_bytes):
-        n = min(step_bytes, src_bytes - o)
-        d_src[o:o + n].copy_(torch.from_numpy(synth.payload(s0 + o, n)))
-    d_dst = torch.empty(dst_bytes, dtype=torch.uint8, device=dev)
+    if in_place:
+        d_src = torch.zeros(src_bytes, dtype=torch.uint8, device=dev)
+        d_dst = d_src
+    else:
+        d_src = torch.empty(src_bytes, dtype=torch.uint8, device=dev)
+        for o in range(0, src_bytes, step_bytes):
+            n = min(step_bytes, src_bytes - o)
+            d_src[o:o + n].copy_(torch.from_numpy(synth.payload(s0 + o, n)))
+        d_dst = torch.empty(dst_bytes, dtype=torch.uint8, device=dev)
     hdr_np = synth.payload(1 << 40, HDR_BYTES)
     d_hdr = torch.from_numpy(hdr_np).to(dev)
     plan = mb.Plan(descs, src_bytes, dst_bytes)
@@ -322,6 +342,11 @@ def run_gpu_arm(args) -> None:
 
     # -- end to end through the public C ABI with HOST (pinned) buffers: H2D + kernels + D2H per step
     e2e_steps = max(2, min(args.steps, 5))
+    if args.kernel_only and in_place:
+        if rank == 0:
+            print(json.dumps({"kernel_ms": round(kernel_ms, 4), "payload_gbs": round(payload / (kernel_ms * 1e-3) / 1e9, 1),
+                              "value": round(value, 1), "kernel_only": True}), flush=True)
+        return
     if args.kernel_only:
         # tuning aid: also time (a) the co-aligned layout (extract slots at the packed source offsets)
         # and (b) one contiguous in-place Cycle over the whole image (config 2 (i))
@@ -348,12 +373,17 @@ def run_gpu_arm(args) -> None:
                               "contiguous_gbs": round(src_bytes / (ms_ct * 1e-3) / 1e9, 1), "value": round(value, 1),
                               "kernel_only": True}), flush=True)
         return
-    h_src = torch.empty(src_bytes, dtype=torch.uint8).pin_memory()
-    h_dst = torch.empty(dst_bytes, dtype=torch.uint8).pin_memory()
+    if in_place:
+        e2e_steps = 2
+        h_src = torch.zeros(src_bytes, dtype=torch.uint8).pin_memory()
+        h_dst = h_src
+    else:
+        h_src = torch.empty(src_bytes, dtype=torch.uint8).pin_memory()
+        h_dst = torch.empty(dst_bytes, dtype=torch.uint8).pin_memory()
+        for o in range(0, src_bytes, step_bytes):
+            n = min(step_bytes, src_bytes - o)
+            h_src[o:o + n].copy_(torch.from_numpy(synth.payload(s0 + o, n)))
     h_hdr = torch.from_numpy(hdr_np.copy()).pin_memory()
-    for o in range(0, src_bytes, step_bytes):
-        n = min(step_bytes, src_bytes - o)
-        h_src[o:o + n].copy_(torch.from_numpy(synth.payload(s0 + o, n)))
 
     def e2e_step():
         mb.cycle(h_hdr.data_ptr() + 4, HDR_BYTES - 4, hdr_key)
@@ -411,16 +441,21 @@ def run_gpu_arm(args) -> None:
     cpu = None
     if world == 1:
         os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core
-        setup = cpu_reference_setup(gdescs, target_seconds=2.0)
+        setup = cpu_reference_setup(gdescs, target_seconds=2.0, payload_fn=payload_fn)
         work = np.empty_like(setup["plain"])
         cpu_reference_step(setup, work)
         secs = min(cpu_reference_step(setup, work) for _ in range(3))
+        if in_place:  # an odd number of passes so far would leave the image ciphered; start from zeros
+            d_src.zero_()
         step()
         torch.cuda.synchronize()
         checked = 0
-        got = d_dst.cpu().numpy()
-        for p, d in zip(setup["parts"], gdescs[:setup["n"]]):
-            o, l, do = int(p["off"]), int(p["len"]), int(d["dst_off"])
+        sample_descs = gdescs[:setup["n"]]
+        d_lo = int(sample_descs["dst_off"].min())
+        d_hi = int((sample_descs["dst_off"] + sample_descs["len"]).max())
+        got = d_dst[d_lo:d_hi].cpu().numpy()
+        for p, d in zip(setup["parts"], sample_descs):
+            o, l, do = int(p["off"]), int(p["len"]), int(d["dst_off"]) - d_lo
             if not np.array_equal(got[do:do + l], work[o:o + l]):
                 raise SystemExit(f"PARITY FAILURE: GPU output differs from the reference cipher at entry src_off={o}")
             checked += l
@@ -432,11 +467,14 @@ def run_gpu_arm(args) -> None:
     line = {
         "metric": "ark_dtb_decrypt_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "scaling": "strong" if in_place else "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic (all-zero payload; throughput is data-independent)" if in_place else "synthetic",
         "config": {"workload": args.workload, "entries_per_gpu": int(len(descs)), "payload_bytes_per_gpu": payload,
-                   "layout": "byte-packed source entries, 16-byte-aligned extract slots, per-entry keys, "
-                             "HDR Cycle + one batched launch per step",
-                   "l2": "inputs (1 GiB read + 1 GiB written per step) exceed the 126 MB L2; no flush needed",
+                   "layout": ("32 parts x 512 MiB, one (offset, len, key) per part, ciphered in place, "
+                              "HDR Cycle + one batched launch per step") if in_place else
+                             ("byte-packed source entries, 16-byte-aligned extract slots, per-entry keys, "
+                              "HDR Cycle + one batched launch per step"),
+                   "l2": "inputs (>= 1 GiB read + written per step) exceed the 126 MB L2; no flush needed",
                    "sharding": "mod_shard_descs offset ranges, no collective" if world > 1 else "single GPU",
                    "host": "rank pinned to its GPU's NUMA-local CPUs (NVML affinity)" if numa_pinned else "default CPU affinity"},
         "roofline": roofline, "cpu_baseline": cpu,
@@ -456,7 +494,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
     ap.add_argument("--kernel-only", action="store_true",
                     help="profiling aid: skip the e2e and CPU-baseline legs (the line then carries nulls)")
     args = ap.parse_args()
