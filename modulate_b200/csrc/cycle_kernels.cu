@@ -14,8 +14,11 @@
 //   * the serial recurrence is broken by modular jump-ahead: per tile a handful of table
 //     multiplies (a^(tile), a^(16*lane), a^(-head)) give each thread the state just before its
 //     chunk; rounds advance by the constant a^512; inside the chunk the state is stepped 16
-//     times with a lazily reduced Mersenne fold (IMAD.WIDE + one add) -- about 4 integer
-//     instructions per payload byte in total;
+//     times with a lazily reduced Mersenne fold (IMAD.WIDE + one add); low bytes are packed
+//     straight from the lazy states and a chunk is redone exactly only if one of its states needed
+//     the canonical subtract (~2^-17 per byte); the chains of the 2-4 chunks a thread has in
+//     flight are generated as one basic block so they interleave -- about 4 integer instructions
+//     per payload byte in total;
 //   * entries are byte-packed (BuildArk leaves no padding), so source and destination are
 //     generally misaligned with respect to each other: the source is read as aligned 16-byte
 //     granules (each lane takes the two granules its chunk straddles; the second is an L1 hit on
@@ -24,7 +27,11 @@
 //     chunk of an entry take a byte path;
 //   * the grid is persistent (SM count x resident CTAs): each warp strides over tiles and
 //     prefetches the next tile's 32-byte record while it streams the current one, so no warp
-//     ever waits on a chain of dependent metadata loads.
+//     ever waits on a chain of dependent metadata loads.  The warp count is kept LOW on purpose
+//     (24-32 per SM): more bytes in flight cost DRAM efficiency (profiles/r01_tuning.md).
+// Alternatives that were built, measured and dropped (register ping-pong, predicate-free group
+// copies, cache hints, L2 bulk prefetch) are in the git history and profiles/r01_tuning.md; the
+// bulk-async (cp.async.bulk + mbarrier) staging ring is kept behind -DMODK_BULK=1.
 #include "cycle_kernels.cuh"
 #include "lcg.h"
 
@@ -58,15 +65,6 @@ using modlcg::low8_canonical;
 #ifndef MODK_INTERLEAVE
 #define MODK_INTERLEAVE 1        // generate the keystream of a whole load group as one basic block (ILP across chunks)
 #endif
-#ifndef MODK_PINGPONG
-#define MODK_PINGPONG 0          // 1: two-stage register software pipeline (next stage's loads before this stage's cipher)
-#endif
-#ifndef MODK_PP_ROUNDS
-#define MODK_PP_ROUNDS 2         // rounds per pipeline stage when MODK_PINGPONG
-#endif
-#ifndef MODK_FULL_GROUPS
-#define MODK_FULL_GROUPS 0       // 1: extra predicate-free code path for fully interior load groups (co-aligned variant); no gain measured
-#endif
 #ifndef MODK_SPECULATE
 #define MODK_SPECULATE 1         // pack low bytes from lazy states, redo the ~1/8000 chunks that needed a canonical subtract
 #endif
@@ -75,12 +73,6 @@ using modlcg::low8_canonical;
 #endif
 #ifndef MODK_STAGES
 #define MODK_STAGES 2            // ring depth per warp (load groups in flight) when MODK_BULK
-#endif
-#ifndef MODK_LD_HINT
-#define MODK_LD_HINT 0           // 0: ld.global   1: .L1::no_allocate on the co-aligned path   2: .cs everywhere
-#endif
-#ifndef MODK_ST_HINT
-#define MODK_ST_HINT 0           // 0: st.global   1: st.global.cs (streaming)
 #endif
 
 static_assert(kIters % MODK_UNROLL == 0 && kIters % MODK_UNROLL_INLINE == 0, "rounds per tile must be a multiple of the unroll");
@@ -99,28 +91,16 @@ constexpr uint32_t kRoundJump = modlcg::pow_a(512);  // one round = 32 lanes x 1
 
 // ---- 128-bit global accesses (explicit state space: the addresses are rebuilt from integers) ------
 
-template <bool kStreamOnce>
 __device__ __forceinline__ uint4 ldg128(uint64_t addr)
 {
     uint4 r;
-    if (MODK_LD_HINT == 2)
-        asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(addr));
-    else if (MODK_LD_HINT == 1 && kStreamOnce)
-        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(addr));
-    else
-        asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(addr));
+    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(addr));
     return r;
 }
 
 __device__ __forceinline__ void stg128(uint64_t addr, const uint4& v)
 {
-    if (MODK_ST_HINT == 1)
-        asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
-    else
-        asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 
 // ---- per-chunk arithmetic -------------------------------------------------------------------
@@ -318,7 +298,7 @@ struct NoHook {
 // kSmem: the group's source granules were staged in shared memory at `stage` (granule j of the
 // group at stage + 16 j) by a bulk-async copy; `after_loads` runs once the data is in registers
 // (the bulk path refills the stage there, before the integer work starts).
-template <int kWs, bool kFull, int kUnroll, bool kSmem = false, typename AfterLoads = NoHook>
+template <int kWs, int kUnroll, bool kSmem = false, typename AfterLoads = NoHook>
 __device__ __forceinline__ uint32_t cipher_group(const TileGeom& g, const uint32_t base, const uint32_t m_hi,
                                                  uint32_t v, const uint32_t lane, const uint32_t bs,
                                                  const uint32_t two, const uint32_t stage = 0u,
@@ -334,7 +314,7 @@ __device__ __forceinline__ uint32_t cipher_group(const TileGeom& g, const uint32
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
         const uint32_t c = base + (uint32_t)u * 32u + lane;
-        fast[u] = kFull || ((c >= g.f_lo) && (c < m_hi));
+        fast[u] = (c >= g.f_lo) && (c < m_hi);
         own[u] = make_uint4(0u, 0u, 0u, 0u);
         nxt[u] = make_uint4(0u, 0u, 0u, 0u);
         if (fast[u]) {
@@ -346,9 +326,9 @@ __device__ __forceinline__ uint32_t cipher_group(const TileGeom& g, const uint32
             } else
 #endif
             {
-                own[u] = ldg128<(kWs < 0)>(sp + 512ull * u);
+                own[u] = ldg128(sp + 512ull * u);
                 if (kWs >= 0)
-                    nxt[u] = ldg128<false>(sp + 512ull * u + 16ull);
+                    nxt[u] = ldg128(sp + 512ull * u + 16ull);
             }
         }
     }
@@ -421,76 +401,6 @@ __device__ __forceinline__ uint32_t cipher_group(const TileGeom& g, const uint32
     return v;
 }
 
-// Software-pipelined form (MODK_PINGPONG): two register stages of kPpRounds rounds each; the loads
-// of the next stage are issued BEFORE the current stage is ciphered, so every warp keeps
-// 512 * kPpRounds bytes in flight at all times and a small number of resident warps is enough.
-// (The loop body is the two-stage ping-pong written out so both register sets have static names.)
-constexpr int kPpRounds = MODK_PP_ROUNDS;
-
-template <int kWs>
-struct PpStage {
-    uint4 own[kPpRounds];
-    uint4 nxt[kPpRounds];
-
-    __device__ __forceinline__ void load(const TileGeom& g, uint32_t base, uint32_t lane, uint32_t m_hi)
-    {
-        const uint64_t sp = g.src_al + 16ull * (base + lane);
-#pragma unroll
-        for (int u = 0; u < kPpRounds; ++u) {
-            const uint32_t c = base + (uint32_t)u * 32u + lane;
-            own[u] = make_uint4(0u, 0u, 0u, 0u);
-            nxt[u] = make_uint4(0u, 0u, 0u, 0u);
-            if ((c >= g.f_lo) && (c < m_hi)) {
-                own[u] = ldg128<(kWs < 0)>(sp + 512ull * u);
-                if (kWs >= 0)
-                    nxt[u] = ldg128<false>(sp + 512ull * u + 16ull);
-            }
-        }
-    }
-
-    __device__ __forceinline__ uint32_t finish(const TileGeom& g, uint32_t base, uint32_t lane, uint32_t m_hi,
-                                               uint32_t v, uint32_t bs, uint32_t two) const
-    {
-        const uint64_t dp = g.dst_al + 16ull * (base + lane);
-#pragma unroll
-        for (int u = 0; u < kPpRounds; ++u) {
-            const uint32_t c = base + (uint32_t)u * 32u + lane;
-            uint4 data = own[u];
-            if (kWs >= 0) {
-                const uint32_t w[8] = {own[u].x, own[u].y, own[u].z, own[u].w, nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
-                constexpr int k = kWs < 0 ? 0 : kWs;
-                data.x = __funnelshift_r(w[k + 0], w[k + 1], bs);
-                data.y = __funnelshift_r(w[k + 1], w[k + 2], bs);
-                data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
-                data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
-            }
-            if ((c >= g.f_lo) && (c < m_hi))
-                stg128(dp + 512ull * u, cycle_chunk(data, v, two));
-            v = mulmod(v, kRoundJump);
-        }
-        return v;
-    }
-};
-
-template <int kWs>
-__device__ __forceinline__ void process_interior_pp(const TileGeom& g, uint32_t v, const uint32_t lane,
-                                                    const uint32_t two)
-{
-    const uint32_t bs = (g.shift & 3u) * 8u;
-    const uint32_t m_hi = min(g.c_end, g.f_hi);
-    constexpr uint32_t kStep = 32u * kPpRounds;
-    PpStage<kWs> sa, sb;
-    uint32_t base = g.c_begin;
-    sa.load(g, base, lane, m_hi);
-#pragma unroll 1
-    for (; base < m_hi; base += 2u * kStep) {
-        sb.load(g, base + kStep, lane, m_hi);  // all predicates false past the end of the tile
-        v = sa.finish(g, base, lane, m_hi, v, bs, two);
-        sa.load(g, base + 2u * kStep, lane, m_hi);
-        v = sb.finish(g, base + kStep, lane, m_hi, v, bs, two);
-    }
-}
-
 template <int kWs, int kUnroll>
 __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, const uint32_t lane,
                                                  const uint32_t two)
@@ -499,19 +409,9 @@ __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, 
     const uint32_t m_hi = min(g.c_end, g.f_hi);
     constexpr uint32_t kGroupChunks = 32u * kUnroll;
 
-    uint32_t base = g.c_begin;
-    if (MODK_FULL_GROUPS && kWs < 0) {  // co-aligned variant only: four more copies would overflow the I-cache
-        if (base < g.f_lo && base < m_hi) {  // the group holding the entry's head edge
-            v = cipher_group<kWs, false, kUnroll>(g, base, m_hi, v, lane, bs, two);
-            base += kGroupChunks;
-        }
 #pragma unroll 1
-        for (; base + kGroupChunks <= m_hi; base += kGroupChunks)
-            v = cipher_group<kWs, true, kUnroll>(g, base, m_hi, v, lane, bs, two);
-    }
-#pragma unroll 1
-    for (; base < m_hi; base += kGroupChunks)
-        v = cipher_group<kWs, false, kUnroll>(g, base, m_hi, v, lane, bs, two);
+    for (uint32_t base = g.c_begin; base < m_hi; base += kGroupChunks)
+        v = cipher_group<kWs, kUnroll>(g, base, m_hi, v, lane, bs, two);
 }
 
 #if MODK_BULK
@@ -563,7 +463,7 @@ __device__ __forceinline__ void process_interior_bulk(const TileGeom& g, uint32_
             if (gi + (uint32_t)kStages < n_groups)
                 issue(gi + (uint32_t)kStages, stage);
         };
-        v = cipher_group<kWs, false, kUnroll, true>(g, base, m_hi, v, lane, bs, two,
+        v = cipher_group<kWs, kUnroll, true>(g, base, m_hi, v, lane, bs, two,
                                                     ring.data + stage * kStageBytes, refill);
     }
     ring.slot = (first_slot + n_groups) % (uint32_t)kStages;
@@ -586,11 +486,7 @@ __device__ __forceinline__ uint32_t tile_start_state(int32_t key, uint32_t h0, u
 #else
 #define MODK_RING_PARAM
 #define MODK_RING_ARG
-#if MODK_PINGPONG
-#define MODK_INTERIOR(K) process_interior_pp<K>(g, v, lane, a.two)
-#else
 #define MODK_INTERIOR(K) process_interior<K, kUnroll>(g, v, lane, a.two)
-#endif
 #endif
 
 template <int kUnroll>
