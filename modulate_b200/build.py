@@ -8,7 +8,9 @@ loaded, importing the compute API raises.
 """
 from __future__ import annotations
 
+import fcntl
 import glob
+import hashlib
 import os
 import shutil
 import subprocess
@@ -44,28 +46,60 @@ def _deps() -> list[str]:
         glob.glob(os.path.join(ROOT, "include", "*.h")) + glob.glob(os.path.join(CSRC, "cli", "*.cpp"))
 
 
+def _fingerprint() -> str:
+    """Content hash of every source the binaries depend on (+ the flags): robust against snapshot
+    copies that do not preserve modification times."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in sorted(_deps()):
+        h.update(os.path.relpath(d, ROOT).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _stamp(target: str) -> str:
+    return target + ".stamp"
+
+
 def stale(target: str) -> bool:
-    if not os.path.exists(target):
+    if not os.path.exists(target) or not os.path.exists(_stamp(target)):
         return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in _deps())
+    with open(_stamp(target)) as f:
+        return f.read().strip() != _fingerprint()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if force or stale(LIB):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-               "-o", LIB, *_sources()]
-        if verbose:
-            print(" ".join(cmd), flush=True)
-        subprocess.check_call(cmd)
-    cli_src = sorted(glob.glob(os.path.join(CSRC, "cli", "*.cpp")))
-    if cli_src and (force or stale(CLI)):
-        os.makedirs(os.path.dirname(CLI), exist_ok=True)
-        cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-               "-o", CLI, *cli_src, "-L", PKG, "-lmodulate_b200", "-Wl,-rpath,$ORIGIN/..", "-ldl", "-pthread"]
-        if verbose:
-            print(" ".join(cmd), flush=True)
-        subprocess.check_call(cmd)
+    """Build (if stale) under an exclusive file lock: several ranks importing at once must not
+    compile into the same output concurrently."""
+    lock_path = os.path.join(PKG, ".build.lock")
+    with open(lock_path, "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            fp = _fingerprint()
+            if force or stale(LIB):
+                tmp = LIB + f".tmp{os.getpid()}"
+                cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+                       "-o", tmp, *_sources()]
+                if verbose:
+                    print(" ".join(cmd), flush=True)
+                subprocess.check_call(cmd)
+                os.replace(tmp, LIB)  # atomic: a process that already mapped the old file keeps it
+                with open(_stamp(LIB), "w") as f:
+                    f.write(fp)
+            cli_src = sorted(glob.glob(os.path.join(CSRC, "cli", "*.cpp")))
+            if cli_src and (force or stale(CLI)):
+                os.makedirs(os.path.dirname(CLI), exist_ok=True)
+                tmp = CLI + f".tmp{os.getpid()}"
+                cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+                       "-o", tmp, *cli_src, "-L", PKG, "-lmodulate_b200", "-Wl,-rpath,$ORIGIN/..", "-ldl", "-pthread"]
+                if verbose:
+                    print(" ".join(cmd), flush=True)
+                subprocess.check_call(cmd)
+                os.replace(tmp, CLI)
+                with open(_stamp(CLI), "w") as f:
+                    f.write(fp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
