@@ -19,6 +19,9 @@ CLI = os.path.join(ROOT, "modulate_b200", "bin", "modulate")
 
 
 def run(cwd, *args, expect=0):
+    if not os.path.exists(CLI):
+        from modulate_b200 import build as _build
+        _build.build()
     assert os.path.exists(CLI), "modulate CLI not built (python -m modulate_b200.build)"
     out = subprocess.run([CLI, *args], cwd=cwd, capture_output=True, text=True, timeout=600)
     assert out.returncode == (0 if expect == 0 else 255), out.stdout + out.stderr
