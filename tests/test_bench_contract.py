@@ -1,0 +1,50 @@
+"""The bench.py JSON contract: reference arm on CPU here, the GPU arm on the B200 box."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COMMON = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+          "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"}
+
+
+def run_bench(*args, timeout=900):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                         timeout=timeout, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0")
+    assert COMMON <= set(d) and d["impl"] == "reference"
+    assert d["unit"] == "GB/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["config"]["workload"] == "cfg2" and d["dtype"] == "u8"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+
+
+@pytest.mark.gpu
+def test_gpu_arm_line():
+    d = run_bench("--steps", "5", "--warmup", "3")
+    assert COMMON | {"roofline", "clocks"} <= set(d) and "impl" not in d
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["scaling"] == "weak"
+    assert d["config"]["workload"] == "cfg2" and d["dtype"] == "u8" and d["data"] == "synthetic"
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["algorithmic_bytes_per_launch"] == 2 * d["config"]["payload_bytes_per_gpu"]
+    assert 0.3 < r["frac"] < 1.2
+    assert d["gpu_launches"] == 2 * d["steps"]          # HDR Cycle + one batched launch per step
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > d["config"]["payload_bytes_per_gpu"] and e["d2h_bytes_per_step"] > 0
+    assert 0 < e["value"] < d["value"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["gpu_bytes_checked_against_it"] > 0
+    assert d["clocks"]["sm_max_mhz"] and isinstance(d["clocks"]["reasons"], list)
