@@ -62,6 +62,12 @@ using modlcg::low8_canonical;
 #ifndef MODK_GRID_MODE
 #define MODK_GRID_MODE 0         // 0: persistent grid (SMs x resident CTAs), 1: one tile per warp, CTAs retire
 #endif
+#ifndef MODK_PIPELINE
+#define MODK_PIPELINE 0          // batched kernel: 1 = two-stage register pipeline (next group's loads before this group's cipher)
+#endif
+#ifndef MODK_PIPELINE_INLINE
+#define MODK_PIPELINE_INLINE 0   // contiguous kernel: same
+#endif
 #ifndef MODK_INTERLEAVE
 #define MODK_INTERLEAVE 1        // generate the keystream of a whole load group as one basic block (ILP across chunks)
 #endif
@@ -75,7 +81,8 @@ using modlcg::low8_canonical;
 #define MODK_STAGES 2            // ring depth per warp (load groups in flight) when MODK_BULK
 #endif
 
-static_assert(kIters % MODK_UNROLL == 0 && kIters % MODK_UNROLL_INLINE == 0, "rounds per tile must be a multiple of the unroll");
+static_assert(kIters % (MODK_UNROLL * (MODK_PIPELINE ? 2 : 1)) == 0 && kIters % MODK_UNROLL_INLINE == 0,
+              "rounds per tile must be a multiple of the unroll (twice the unroll when pipelined)");
 
 // tile index within an entry < 2^32 / kTileBytes + 1; split 10 bits low / rest high
 constexpr int kTw0Size = 1024;
@@ -291,117 +298,118 @@ __device__ __noinline__ void edge_chunk(const uint8_t* src_entry, uint8_t* dst_e
 // starts kWs words (+ a runtime 0..3 bytes) into its first granule and straddles two.
 // kFull: every chunk of the group is interior, so there are no per-lane predicates and all
 // addresses are one 64-bit pointer per lane plus immediates.
-struct NoHook {
-    __device__ __forceinline__ void operator()() const {}
-};
-
-// kSmem: the group's source granules were staged in shared memory at `stage` (granule j of the
-// group at stage + 16 j) by a bulk-async copy; `after_loads` runs once the data is in registers
-// (the bulk path refills the stage there, before the integer work starts).
-template <int kWs, int kUnroll, bool kSmem = false, typename AfterLoads = NoHook>
-__device__ __forceinline__ uint32_t cipher_group(const TileGeom& g, const uint32_t base, const uint32_t m_hi,
-                                                 uint32_t v, const uint32_t lane, const uint32_t bs,
-                                                 const uint32_t two, const uint32_t stage = 0u,
-                                                 AfterLoads after_loads = AfterLoads())
-{
+// The source granules of one load group (kUnroll rounds) held in registers, and the two halves of
+// working on them: `load` (global memory, or a shared-memory stage filled by a bulk-async copy) and
+// `finish` (keystream, re-alignment, XOR, store).
+template <int kWs, int kUnroll>
+struct GroupRegs {
     uint4 own[kUnroll];
     uint4 nxt[kUnroll];
-    bool fast[kUnroll];
-    const uint64_t sp = g.src_al + 16ull * (base + lane);
-    const uint64_t dp = g.dst_al + 16ull * (base + lane);
 
-    // phase 1: every load of the unrolled group is issued before anything consumes one
+    // every load of the group is issued before anything consumes one
+    template <bool kSmem>
+    __device__ __forceinline__ void load(const TileGeom& g, const uint32_t base, const uint32_t m_hi,
+                                         const uint32_t lane, const uint32_t stage)
+    {
+        const uint64_t sp = g.src_al + 16ull * (base + lane);
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-        const uint32_t c = base + (uint32_t)u * 32u + lane;
-        fast[u] = (c >= g.f_lo) && (c < m_hi);
-        own[u] = make_uint4(0u, 0u, 0u, 0u);
-        nxt[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (fast[u]) {
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t c = base + (uint32_t)u * 32u + lane;
+            own[u] = make_uint4(0u, 0u, 0u, 0u);
+            nxt[u] = make_uint4(0u, 0u, 0u, 0u);
+            if ((c >= g.f_lo) && (c < m_hi)) {
 #if MODK_BULK
-            if (kSmem) {
-                own[u] = lds128(stage + 16u * (32u * (uint32_t)u + lane));
-                if (kWs >= 0)
-                    nxt[u] = lds128(stage + 16u * (32u * (uint32_t)u + lane) + 16u);
-            } else
+                if (kSmem) {
+                    own[u] = lds128(stage + 16u * (32u * (uint32_t)u + lane));
+                    if (kWs >= 0)
+                        nxt[u] = lds128(stage + 16u * (32u * (uint32_t)u + lane) + 16u);
+                } else
 #endif
-            {
-                own[u] = ldg128(sp + 512ull * u);
-                if (kWs >= 0)
-                    nxt[u] = ldg128(sp + 512ull * u + 16ull);
+                {
+                    own[u] = ldg128(sp + 512ull * u);
+                    if (kWs >= 0)
+                        nxt[u] = ldg128(sp + 512ull * u + 16ull);
+                }
             }
         }
     }
-    after_loads();
 
-#if MODK_INTERLEAVE
-    // phase 2a: the kUnroll keystream chunks of the group, generated as ONE basic block so that the
-    // independent 16-step chains interleave (ILP = kUnroll) instead of running one after another;
-    // low bytes are packed straight from the lazy states and the states are OR-ed (see cycle_chunk)
-    uint32_t st[kUnroll];
-    uint32_t v0[kUnroll];
-#pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-        v0[u] = v;
-        st[u] = v;
-        v = mulmod(v, kRoundJump);  // state just before this lane's chunk of the next round
+    __device__ __forceinline__ uint4 aligned(const int u, const uint32_t bs) const
+    {
+        uint4 data = own[u];
+        if (kWs >= 0) {
+            const uint32_t w[8] = {own[u].x, own[u].y, own[u].z, own[u].w, nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
+            constexpr int k = kWs < 0 ? 0 : kWs;
+            data.x = __funnelshift_r(w[k + 0], w[k + 1], bs);
+            data.y = __funnelshift_r(w[k + 1], w[k + 2], bs);
+            data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
+            data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
+        }
+        return data;
     }
-    uint32_t ks[kUnroll][4];
-    uint32_t any = 0u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
+
+    // returns the state advanced by kUnroll rounds
+    __device__ __forceinline__ uint32_t finish(const TileGeom& g, const uint32_t base, const uint32_t m_hi, uint32_t v,
+                                               const uint32_t lane, const uint32_t bs, const uint32_t two) const
+    {
+        const uint64_t dp = g.dst_al + 16ull * (base + lane);
+#if MODK_INTERLEAVE
+        // the kUnroll keystream chunks of the group, generated as ONE basic block so that the
+        // independent 16-step chains interleave (ILP = kUnroll) instead of running one after another;
+        // low bytes are packed straight from the lazy states and the states are OR-ed (see cycle_chunk)
+        uint32_t st[kUnroll];
+        uint32_t v0[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
-            const uint32_t b0 = step_lazy(st[u]);
-            const uint32_t b1 = step_lazy(b0);
-            const uint32_t b2 = step_lazy(b1);
-            const uint32_t b3 = step_lazy(b2);
-            st[u] = b3;
-            any |= b0 | b1;
-            any |= b2 | b3;
-            ks[u][j] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+            v0[u] = v;
+            st[u] = v;
+            v = mulmod(v, kRoundJump);  // state just before this lane's chunk of the next round
         }
-    }
-    // phase 2b: re-align, apply, store
+        uint32_t ks[kUnroll][4];
+        uint32_t any = 0u;
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-        uint4 data = own[u];
-        if (kWs >= 0) {
-            const uint32_t w[8] = {own[u].x, own[u].y, own[u].z, own[u].w, nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
-            constexpr int k = kWs < 0 ? 0 : kWs;
-            data.x = __funnelshift_r(w[k + 0], w[k + 1], bs);
-            data.y = __funnelshift_r(w[k + 1], w[k + 2], bs);
-            data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
-            data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const uint32_t b0 = step_lazy(st[u]);
+                const uint32_t b1 = step_lazy(b0);
+                const uint32_t b2 = step_lazy(b1);
+                const uint32_t b3 = step_lazy(b2);
+                st[u] = b3;
+                any |= b0 | b1;
+                any |= b2 | b3;
+                ks[u][j] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+            }
         }
-        uint4 out = make_uint4(data.x ^ ks[u][0], data.y ^ ks[u][1], data.z ^ ks[u][2], data.w ^ ks[u][3]);
-        if (__builtin_expect((int32_t)any < 0, 0))  // some state of some chunk needed a canonical subtract: redo exactly
-            out = cycle_chunk_rare(data, v0[u], two);
-        if (fast[u])
-            stg128(dp + 512ull * u, out);
-    }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t c = base + (uint32_t)u * 32u + lane;
+            const uint4 data = aligned(u, bs);
+            uint4 out = make_uint4(data.x ^ ks[u][0], data.y ^ ks[u][1], data.z ^ ks[u][2], data.w ^ ks[u][3]);
+            if (__builtin_expect((int32_t)any < 0, 0))  // some state of the group needed a canonical subtract: redo exactly
+                out = cycle_chunk_rare(data, v0[u], two);
+            if ((c >= g.f_lo) && (c < m_hi))
+                stg128(dp + 512ull * u, out);
+        }
 #else
-    // phase 2: re-align, cipher, store
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-        uint4 data = own[u];
-        if (kWs >= 0) {
-            const uint32_t w[8] = {own[u].x, own[u].y, own[u].z, own[u].w, nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
-            constexpr int k = kWs < 0 ? 0 : kWs;
-            data.x = __funnelshift_r(w[k + 0], w[k + 1], bs);
-            data.y = __funnelshift_r(w[k + 1], w[k + 2], bs);
-            data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
-            data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t c = base + (uint32_t)u * 32u + lane;
+            if ((c >= g.f_lo) && (c < m_hi))
+                stg128(dp + 512ull * u, cycle_chunk(aligned(u, bs), v, two));
+            v = mulmod(v, kRoundJump);
         }
-        if (fast[u])
-            stg128(dp + 512ull * u, cycle_chunk(data, v, two));
-        v = mulmod(v, kRoundJump);  // state just before this lane's chunk of the next round
-    }
 #endif
-    return v;
-}
+        return v;
+    }
+};
 
-template <int kWs, int kUnroll>
+// Interior chunks of the tile.  kWs < 0: source and destination are co-aligned (one load per
+// chunk).  kWs in 0..3: the chunk starts kWs words (+ a runtime 0..3 bytes) into its first granule
+// and straddles two.  kPipelined: two register stages -- the loads of group i+1 are issued before
+// group i is ciphered and stored, so a warp has loads in flight during its integer work (the loop
+// body is the two-stage ping-pong written out so both register sets have static names).
+template <int kWs, int kUnroll, bool kPipelined>
 __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, const uint32_t lane,
                                                  const uint32_t two)
 {
@@ -409,9 +417,26 @@ __device__ __forceinline__ void process_interior(const TileGeom& g, uint32_t v, 
     const uint32_t m_hi = min(g.c_end, g.f_hi);
     constexpr uint32_t kGroupChunks = 32u * kUnroll;
 
+    if (kPipelined) {
+        GroupRegs<kWs, kUnroll> ra, rb;
+        uint32_t base = g.c_begin;
+        if (base < m_hi)
+            ra.template load<false>(g, base, m_hi, lane, 0u);
 #pragma unroll 1
-    for (uint32_t base = g.c_begin; base < m_hi; base += kGroupChunks)
-        v = cipher_group<kWs, kUnroll>(g, base, m_hi, v, lane, bs, two);
+        for (; base < m_hi; base += 2u * kGroupChunks) {
+            rb.template load<false>(g, base + kGroupChunks, m_hi, lane, 0u);  // all predicates false past the tile
+            v = ra.finish(g, base, m_hi, v, lane, bs, two);
+            ra.template load<false>(g, base + 2u * kGroupChunks, m_hi, lane, 0u);
+            v = rb.finish(g, base + kGroupChunks, m_hi, v, lane, bs, two);
+        }
+    } else {
+#pragma unroll 1
+        for (uint32_t base = g.c_begin; base < m_hi; base += kGroupChunks) {
+            GroupRegs<kWs, kUnroll> r;
+            r.template load<false>(g, base, m_hi, lane, 0u);
+            v = r.finish(g, base, m_hi, v, lane, bs, two);
+        }
+    }
 }
 
 #if MODK_BULK
@@ -458,13 +483,12 @@ __device__ __forceinline__ void process_interior_bulk(const TileGeom& g, uint32_
             mbar_wait(ring.bars + 8u * stage, (ring.phases >> stage) & 1u);
             ring.phases ^= 1u << stage;
         }
-        auto refill = [&]() {
-            __syncwarp();  // every lane holds its granules in registers: the stage may be overwritten
-            if (gi + (uint32_t)kStages < n_groups)
-                issue(gi + (uint32_t)kStages, stage);
-        };
-        v = cipher_group<kWs, kUnroll, true>(g, base, m_hi, v, lane, bs, two,
-                                                    ring.data + stage * kStageBytes, refill);
+        GroupRegs<kWs, kUnroll> r;
+        r.template load<true>(g, base, m_hi, lane, ring.data + stage * kStageBytes);
+        __syncwarp();  // every lane holds its granules in registers: the stage may be overwritten
+        if (gi + (uint32_t)kStages < n_groups)
+            issue(gi + (uint32_t)kStages, stage);
+        v = r.finish(g, base, m_hi, v, lane, bs, two);
     }
     ring.slot = (first_slot + n_groups) % (uint32_t)kStages;
 }
@@ -486,10 +510,10 @@ __device__ __forceinline__ uint32_t tile_start_state(int32_t key, uint32_t h0, u
 #else
 #define MODK_RING_PARAM
 #define MODK_RING_ARG
-#define MODK_INTERIOR(K) process_interior<K, kUnroll>(g, v, lane, a.two)
+#define MODK_INTERIOR(K) process_interior<K, kUnroll, kPipelined>(g, v, lane, a.two)
 #endif
 
-template <int kUnroll>
+template <int kUnroll, bool kPipelined>
 __device__ __forceinline__ void run_tile(const BatchArgs& a, const uint64_t src_off, const uint64_t dst_off,
                                          const uint32_t len, const uint32_t st, const uint32_t c_begin,
                                          const uint32_t tile_chunks, const uint32_t lane MODK_RING_PARAM)
@@ -600,7 +624,7 @@ __global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_ker
         TileRec nxt = cur;
         if (more)
             nxt = load_tile_rec(a.tiles + tile + stride);
-        run_tile<MODK_UNROLL>(a, cur.src_off, cur.dst_off, cur.len, cur.state, cur.tin * (uint32_t)kChunksPerTile,
+        run_tile<MODK_UNROLL, (MODK_PIPELINE != 0)>(a, cur.src_off, cur.dst_off, cur.len, cur.state, cur.tin * (uint32_t)kChunksPerTile,
                  (uint32_t)kChunksPerTile, lane MODK_RING_ARG);
         if (!more)
             break;
@@ -627,7 +651,7 @@ cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
         const uint32_t h0 = (uint32_t)((uint64_t)a.dst + d.dst_off) & 15u;
         const uint32_t st = mulmod(tile_start_state(d.key, h0, round0 / (uint32_t)kIters),
                                    c_round_pow[round0 % (uint32_t)kIters]);
-        run_tile<MODK_UNROLL_INLINE>(a, d.src_off, d.dst_off, d.len, st, round0 * 32u, a.rounds_per_tile * 32u, lane MODK_RING_ARG);
+        run_tile<MODK_UNROLL_INLINE, (MODK_PIPELINE_INLINE != 0)>(a, d.src_off, d.dst_off, d.len, st, round0 * 32u, a.rounds_per_tile * 32u, lane MODK_RING_ARG);
         if ((a.n_tiles - tile) <= stride)
             break;
         tile += stride;
