@@ -2,6 +2,7 @@
 // Out-of-place copy of 1 GiB (read 1 GiB + write 1 GiB), several work decompositions, CUDA events.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/copy_skeleton_bench tools/copy_skeleton_bench.cu
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 // A: grid-stride, thread-interleaved: consecutive threads consecutive 16 B, U loads in flight,
@@ -138,7 +139,7 @@ float time_ms(F launch, int reps)
     return ms / reps;
 }
 
-int main()
+int main(int argc, char** argv)
 {
     const size_t bytes = 1ull << 30, n = bytes / 16;
     uint4 *s, *d;
@@ -148,6 +149,16 @@ int main()
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     auto report = [&](const char* name, float ms) { printf("%-44s %7.1f GB/s (read+write)\n", name, 2.0 * bytes / ms / 1e6); };
+    if (argc >= 3) {  // sustained mode: copy_skeleton_bench <B|C|M> <reps>  (sample power / clocks from outside)
+        const int n_reps = atoi(argv[2]);
+        const char which = argv[1][0];
+        float ms = 0;
+        if (which == 'B') ms = time_ms([&] { k_blockchunk<4><<<(unsigned)((n + 1023) / 1024), 256>>>(s, d, n); }, n_reps);
+        else if (which == 'C') ms = time_ms([&] { k_warptile<4, 16><<<sms * 3, 256>>>(s, d, n); }, n_reps);
+        else ms = time_ms([&] { cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice); }, n_reps);
+        printf("sustained %c x %d: %.1f GB/s\n", which, n_reps, 2.0 * bytes / ms / 1e6);
+        return 0;
+    }
     const int reps = 30;
     report("cudaMemcpy D2D", time_ms([&] { cudaMemcpyAsync(d, s, bytes, cudaMemcpyDeviceToDevice); }, reps));
     for (int bps : {2, 4, 8}) {
