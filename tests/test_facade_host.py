@@ -218,3 +218,19 @@ def test_header_fuzz_never_crashes(cli, tmp_path):
         if out.returncode not in (0, 255):
             crashes.append((trial, kind, out.returncode))
     assert not crashes, crashes
+
+
+def test_external_caller_compiles_against_facade_headers(cli, tmp_path):
+    """A caller that only includes the facade headers (reference class names and signatures)."""
+    exe = os.path.join(BUILD, "facade_sample")
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cpp"))) + [os.path.join(ROOT, "tests", "cpp", "facade_sample.cpp"),
+                                                              os.path.join(ROOT, "tests", "cpp", "mock_abi.cpp")]
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-Wall", "-pthread", "-I", CSRC, "-I", os.path.join(ROOT, "include"),
+                           "-o", exe, *srcs, "-L", os.path.join(ROOT, "oracle"), "-loracle",
+                           f"-Wl,-rpath,{os.path.join(ROOT, 'oracle')}"])
+    hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), n_files=25, n_parts=2, seed=41)
+    out = subprocess.run([exe, "main_ps4.hdr", "out/"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "keystream: 7a cc ad 6f af 91 a7 e3" in out.stdout          # PS4 key KAT (SURVEY.md 8(c))
+    assert f"files: {len(hdr.entries)}, has first: 1" in out.stdout
+    check_unpacked(tmp_path / "out", hdr, payloads)
