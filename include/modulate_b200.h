@@ -18,9 +18,12 @@
  *     otherwise; mod_last_error() returns a thread-local human-readable message.
  *   - There is NO CPU fallback.  If no CUDA device / driver is usable, compute entry points
  *     return MOD_ERR_CUDA and the C++ facade aborts loudly (the reference's Cycle is void).
- *   - One process drives one GPU (mod_init binds it); multi-GPU runs are one process per GPU
- *     with the work split by mod_shard_descs / mod_shard_range -- shards are independent, so
- *     no collective is needed.
+ *   - Every visible GPU has its own context inside the library (streams, HBM workspaces, jump
+ *     tables); nothing is torn down when a thread switches devices.  Single-device entry points
+ *     work on the calling thread's current CUDA device (mod_init(d) sets it); the *_sharded entry
+ *     points split one call over several GPUs inside ONE process (one host thread + stream set per
+ *     device).  One process per GPU with the work split by mod_shard_descs
+ *     / mod_shard_range works equally well -- shards are independent, so no collective is needed.
  *   - "stream" parameters are a cudaStream_t passed as void* (NULL = the legacy default stream).
  *     Functions taking a stream are asynchronous; the others return after the result is visible
  *     to the caller, which preserves Cycle's in-place contract.
@@ -41,7 +44,7 @@ extern "C" {
 #define MOD_ERR_ALIGN (-3)     /* plan was built for a different dst alignment (dst & 15) */
 #define MOD_ERR_NOMEM (-4)     /* host or device allocation failed */
 
-#define MOD_ABI_VERSION 1
+#define MOD_ABI_VERSION 2
 
 /* One archive entry / stream piece: copy `len` bytes from src+src_off to dst+dst_off while XORing
  * them with the keystream of CEncryptionCycler::Cycle(., len, key), the stream restarting at the
@@ -72,13 +75,15 @@ uint64_t mod_launch_count(void);
 
 /* ---- memory helpers ---------------------------------------------------------------------- */
 
-void* mod_host_alloc(uint64_t bytes); /* pinned (page-locked) host memory; NULL on failure */
+void* mod_host_alloc(uint64_t bytes); /* pinned (page-locked, portable across devices) host memory; NULL on failure */
 int mod_host_free(void* p);
 void* mod_device_alloc(uint64_t bytes); /* HBM; NULL on failure */
 int mod_device_free(void* p);
 int mod_memcpy_h2d(void* d_dst, const void* h_src, uint64_t bytes, void* stream);
 int mod_memcpy_d2h(void* h_dst, const void* d_src, uint64_t bytes, void* stream);
 int mod_stream_sync(void* stream);
+void* mod_stream_create(void); /* non-blocking stream on the current device; NULL on failure */
+int mod_stream_destroy(void* stream);
 
 /* ---- CEncryptionCycler::Cycle ------------------------------------------------------------ */
 
@@ -88,6 +93,13 @@ int mod_stream_sync(void* stream);
  * 64-bit: streams longer than the reference's 32-bit length continue the same keystream
  * (period 2^31-2). */
 int mod_cycle(void* data, uint64_t len, int32_t key);
+
+/* mod_cycle on a HOST buffer split by offset range over several GPUs of this process: device g of
+ * the G selected ones ciphers bytes mod_shard_range(len, g, G) starting from the jumped key
+ * (mod_key_jump), each on its own host thread and stream set; returns when every range is back in
+ * `data`.  `dev_mask` bit d selects CUDA device d; 0 = every visible device.  Lifts the reference's
+ * single-threaded, 32-bit-length Cycle (CEncryptionCycler.h:6) to a whole node. */
+int mod_cycle_sharded(void* data, uint64_t len, int32_t key, uint64_t dev_mask);
 
 /* Device-resident, asynchronous on `stream`.  d_src == d_dst is the in-place form; otherwise the
  * ranges must not overlap.  No alignment requirement on either pointer. */
@@ -115,11 +127,32 @@ uint64_t mod_plan_num_tiles(const mod_plan* plan);
  * Asynchronous on `stream`.  d_src == d_dst with src_off == dst_off is the in-place form. */
 int mod_plan_run(const mod_plan* plan, const void* d_src, void* d_dst, void* stream);
 
+/* Tiles [*tile_begin, *tile_end) of the plan that belong to descriptors [entry_begin, entry_end). */
+int mod_plan_tile_range(const mod_plan* plan, uint64_t entry_begin, uint64_t entry_end, uint64_t* tile_begin,
+                        uint64_t* tile_end);
+
+/* Run tiles [tile_begin, tile_end) of the plan with only a WINDOW of each buffer resident: bytes
+ * [src_win_off, +src_win_bytes) of the plan's source space live at d_src_win and bytes
+ * [dst_win_off, +dst_win_bytes) of its destination space at d_dst_win ((d_dst_win - dst_win_off) & 15
+ * must equal the plan's dst_align).  Every byte the tile range touches must lie inside the windows
+ * (checked on the host).  This is what lets a caller stream an archive through a ring of slot
+ * buffers with ONE plan -- CArk::ExtractFiles / BuildArk do (the reference holds the whole image in
+ * one allocation, CArk.cpp:738, :780).  Asynchronous on `stream`. */
+int mod_plan_run_window(const mod_plan* plan, uint64_t tile_begin, uint64_t tile_end, const void* d_src_win,
+                        uint64_t src_win_off, uint64_t src_win_bytes, void* d_dst_win, uint64_t dst_win_off,
+                        uint64_t dst_win_bytes, void* stream);
+
 /* Convenience: plan + run + destroy, synchronous.  `src` / `dst` are both host pointers (staged
  * through HBM in groups of entries, upload / kernel / download overlapped) or both device pointers.
  * In both forms bytes of dst that no descriptor covers keep their value. */
 int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t src_bytes,
                     void* dst, uint64_t dst_bytes);
+
+/* mod_cycle_batch on HOST buffers split over several GPUs of this process: the descriptor list is
+ * cut into equal-payload shards (mod_shard_descs) and each selected device streams its shard on its
+ * own host thread and stream set.  `dev_mask` as for mod_cycle_sharded. */
+int mod_cycle_batch_sharded(const mod_desc* descs, uint64_t n, const void* src, uint64_t src_bytes,
+                            void* dst, uint64_t dst_bytes, uint64_t dev_mask);
 
 /* ---- offset-range sharding (host logic, no GPU needed) -------------------------------------- */
 

@@ -9,13 +9,14 @@ over that C ABI, mirroring the reference's operator interface for the path:
   ``CEncryptionCycler.h:6``; in place, host or device buffer.
 * ``Plan`` / ``cycle_batch`` -- CArk's offset/length table as device descriptors (reference
   ``CArk.cpp:494`` gather, ``:807-811`` scatter) through one variable-length batched kernel.
-* ``shard_range`` / ``shard_descs`` / ``key_jump`` -- offset-range sharding, one process per GPU.
+* ``shard_range`` / ``shard_descs`` / ``key_jump`` -- offset-range sharding, one process per GPU;
+  ``cycle_sharded`` / ``cycle_batch_sharded`` -- the same split over every GPU inside ONE process.
 
 Nothing here computes keystream on the CPU; every call goes through the CUDA library and raises
 ``ModError`` if no GPU is usable.
 """
-from .api import (CEncryptionCycler, DESC_DTYPE, ModError, Plan, cycle, cycle_batch, cycle_device,
-                  device_count, init, key_jump, launch_count, make_descs, shard_descs, shard_range)
+from .api import (CEncryptionCycler, DESC_DTYPE, ModError, Plan, cycle, cycle_batch, cycle_batch_sharded,
+                  cycle_device, cycle_sharded, device_count, init, key_jump, launch_count, make_descs, shard_descs, shard_range)
 
-__all__ = ["CEncryptionCycler", "DESC_DTYPE", "ModError", "Plan", "cycle", "cycle_batch", "cycle_device",
+__all__ = ["CEncryptionCycler", "DESC_DTYPE", "ModError", "Plan", "cycle", "cycle_batch", "cycle_batch_sharded", "cycle_device", "cycle_sharded",
            "device_count", "init", "key_jump", "launch_count", "make_descs", "shard_descs", "shard_range"]

@@ -39,7 +39,10 @@ SIGNATURES = {
     "mod_memcpy_h2d": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]),
     "mod_memcpy_d2h": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]),
     "mod_stream_sync": (ctypes.c_int, [ctypes.c_void_p]),
+    "mod_stream_create": (ctypes.c_void_p, []),
+    "mod_stream_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "mod_cycle": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32]),
+    "mod_cycle_sharded": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32, ctypes.c_uint64]),
     "mod_cycle_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32,
                                         ctypes.c_void_p]),
     "mod_key_jump": (ctypes.c_int32, [ctypes.c_int32, ctypes.c_uint64]),
@@ -49,8 +52,15 @@ SIGNATURES = {
     "mod_plan_payload_bytes": (ctypes.c_uint64, [ctypes.c_void_p]),
     "mod_plan_num_tiles": (ctypes.c_uint64, [ctypes.c_void_p]),
     "mod_plan_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mod_plan_tile_range": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64,
+                                           ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "mod_plan_run_window": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p,
+                                           ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
+                                           ctypes.c_uint64, ctypes.c_void_p]),
     "mod_cycle_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
                                        ctypes.c_void_p, ctypes.c_uint64]),
+    "mod_cycle_batch_sharded": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
+                                               ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]),
     "mod_shard_range": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
                                        ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "mod_shard_descs": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
@@ -79,7 +89,12 @@ def load() -> ctypes.CDLL:
                     f"({exc}); there is no CPU fallback") from exc
     L = ctypes.CDLL(_LIB_PATH)
     for name, (restype, argtypes) in SIGNATURES.items():
-        fn = getattr(L, name)  # AttributeError here = header/library mismatch: fail loudly
+        try:
+            fn = getattr(L, name)
+        except AttributeError:
+            if _LIB_PATH != _build.LIB:  # an older tuning variant selected through MODULATE_B200_LIB
+                continue
+            raise  # header / library mismatch in the product build: fail loudly
         fn.restype = restype
         fn.argtypes = argtypes
     _lib = L

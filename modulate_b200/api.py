@@ -71,6 +71,19 @@ def cycle(buf: Any, size: Optional[int], key: int) -> None:
     _abi.check(_abi.load().mod_cycle(addr, int(size), _i32(key)))
 
 
+def cycle_sharded(buf: Any, size: Optional[int], key: int, dev_mask: int = 0) -> None:
+    """``Cycle`` on a HOST buffer split by offset range over the GPUs ``dev_mask`` selects (0 = all
+    visible), one host thread + stream set per device inside this process (synchronous)."""
+    addr, nbytes, is_cuda = _buffer_info(buf)
+    if is_cuda:
+        raise ValueError("cycle_sharded takes a host buffer")
+    if size is None:
+        size = nbytes
+    if nbytes >= 0 and size > nbytes:
+        raise ValueError(f"liDataSize {size} exceeds the {nbytes}-byte buffer")
+    _abi.check(_abi.load().mod_cycle_sharded(addr, int(size), _i32(key), int(dev_mask)))
+
+
 def cycle_device(src: Any, dst: Any, size: int, key: int, stream: int = 0) -> None:
     """Asynchronous device-resident Cycle (src may equal dst)."""
     s_addr, s_n, _ = _buffer_info(src)
@@ -127,6 +140,22 @@ class Plan:
         d_addr, _, _ = _buffer_info(dst)
         _abi.check(self._lib.mod_plan_run(self._handle, s_addr, d_addr, stream or None))
 
+    def tile_range(self, entry_begin: int, entry_end: int) -> Tuple[int, int]:
+        """Tiles that belong to descriptors [entry_begin, entry_end)."""
+        t0, t1 = ctypes.c_uint64(), ctypes.c_uint64()
+        _abi.check(self._lib.mod_plan_tile_range(self._handle, int(entry_begin), int(entry_end),
+                                                 ctypes.byref(t0), ctypes.byref(t1)))
+        return int(t0.value), int(t1.value)
+
+    def run_window(self, tile_begin: int, tile_end: int, src_win: Any, src_win_off: int, src_win_bytes: int,
+                   dst_win: Any, dst_win_off: int, dst_win_bytes: int, stream: int = 0) -> None:
+        """Run a tile sub-range with only a window of each buffer resident (slot-ring streaming)."""
+        s_addr, _, _ = _buffer_info(src_win)
+        d_addr, _, _ = _buffer_info(dst_win)
+        _abi.check(self._lib.mod_plan_run_window(self._handle, int(tile_begin), int(tile_end), s_addr,
+                                                 int(src_win_off), int(src_win_bytes), d_addr, int(dst_win_off),
+                                                 int(dst_win_bytes), stream or None))
+
     def close(self) -> None:
         if self._handle:
             self._lib.mod_plan_destroy(self._handle)
@@ -151,6 +180,21 @@ def cycle_batch(descs: np.ndarray, src: Any, dst: Any, src_bytes: Optional[int] 
         raise ValueError("buffer sizes are required with raw addresses")
     _abi.check(_abi.load().mod_cycle_batch(d.ctypes.data if len(d) else None, len(d), s_addr, int(src_bytes),
                                            d_addr, int(dst_bytes)))
+
+
+def cycle_batch_sharded(descs: np.ndarray, src: Any, dst: Any, src_bytes: Optional[int] = None,
+                        dst_bytes: Optional[int] = None, dev_mask: int = 0) -> None:
+    """``cycle_batch`` on HOST buffers with the descriptor list cut into equal-payload shards, one per
+    selected GPU (``dev_mask`` bit d = CUDA device d, 0 = all), inside this process (synchronous)."""
+    d = _descs(descs)
+    s_addr, s_n, _ = _buffer_info(src)
+    d_addr, d_n, _ = _buffer_info(dst)
+    src_bytes = s_n if src_bytes is None else src_bytes
+    dst_bytes = d_n if dst_bytes is None else dst_bytes
+    if src_bytes < 0 or dst_bytes < 0:
+        raise ValueError("buffer sizes are required with raw addresses")
+    _abi.check(_abi.load().mod_cycle_batch_sharded(d.ctypes.data if len(d) else None, len(d), s_addr, int(src_bytes),
+                                                   d_addr, int(dst_bytes), int(dev_mask)))
 
 
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:

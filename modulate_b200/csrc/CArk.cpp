@@ -100,8 +100,9 @@ bool KeepExistingOutput(const std::string& lPath)
 }
 
 // Relative names of every regular file under lRoot (which ends in '/'), files of a directory first,
-// then its sub-directories, each level in case-insensitive name order (the reference walks with
-// FindFirstFileA, Utils.cpp:5-70, whose NTFS order is alphabetical).
+// then its sub-directories, each level in the order NTFS keeps its directory index in: by UPPER-CASED
+// name (the reference walks with FindFirstFileA, Utils.cpp:5-70, and takes whatever order the file
+// system returns; '_' therefore sorts after the letters, not before them).
 void ListFiles(const std::string& lRoot, const std::string& lRelative, std::vector<std::string>& laOut)
 {
     DIR* lpDir = opendir((lRoot + lRelative).c_str());
@@ -121,7 +122,7 @@ void ListFiles(const std::string& lRoot, const std::string& lRelative, std::vect
     closedir(lpDir);
     auto lLess = [](const std::string& lA, const std::string& lB) {
         return std::lexicographical_compare(lA.begin(), lA.end(), lB.begin(), lB.end(), [](char a, char b) {
-            return std::tolower((unsigned char)a) < std::tolower((unsigned char)b);
+            return std::toupper((unsigned char)a) < std::toupper((unsigned char)b);
         });
     };
     std::sort(laFiles.begin(), laFiles.end(), lLess);

@@ -181,18 +181,12 @@ std::vector<unsigned char> CDtaFile::SaveToMemory() const
     std::vector<unsigned char> lOut;
     lOut.push_back(1);
     Put<int32_t>(lOut, 1);
-    bool lbFirst = true;
-    for (const auto& lpTree : maTrees) {
-        if (!lbFirst) {
-            // Load expects (type, word) between top-level trees.  The reference's Save omits them
-            // (CDtaFile.cpp:371-374), which only works for single-tree files; writing them keeps
-            // multi-tree files loadable and is byte-identical for the single-tree case.
-            Put<int32_t>(lOut, lpTree->miType);
-            Put<int32_t>(lOut, 1);
-        }
-        lbFirst = false;
+    // Like the reference's Save (CDtaFile.cpp:371-374) the top-level trees are streamed back to back,
+    // WITHOUT the (type, 1) words Load consumes between them (:93-94): a file with several top-level
+    // trees does not round-trip through the reference, and does not here either -- byte parity with
+    // what the reference writes (tests/golden/dtb/two_trees) wins over repairing its format.
+    for (const auto& lpTree : maTrees)
         WriteTree(lOut, *lpTree);
-    }
     return lOut;
 }
 

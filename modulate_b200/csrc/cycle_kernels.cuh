@@ -7,17 +7,20 @@
 namespace modk {
 
 // Geometry of the work decomposition.  A "chunk" is one 16-byte, 16-byte-aligned piece of the
-// DESTINATION address space; a "tile" is what one warp processes at a time: kIters rounds of 32
-// chunks (8 KiB of destination with the default kIters = 16).
-#ifndef MODK_ITERS
-#define MODK_ITERS 16
+// DESTINATION address space; a "tile" is what one CTA processes before it retires: kUnroll rounds
+// of kThreadsPerCta consecutive chunks, i.e. one contiguous 8 KiB span of one entry with the defaults.
+#ifndef MODK_THREADS
+#define MODK_THREADS 128
 #endif
-constexpr int kIters = MODK_ITERS;
-constexpr int kChunksPerTile = 32 * kIters;           // 512 chunks
-constexpr uint32_t kTileBytes = 16u * kChunksPerTile;  // 8 KiB of destination per tile
-constexpr int kWarpsPerCta = 8;
-constexpr int kThreadsPerCta = 32 * kWarpsPerCta;
+#ifndef MODK_UNROLL
+#define MODK_UNROLL 4
+#endif
+constexpr int kThreadsPerCta = MODK_THREADS;
+constexpr int kUnroll = MODK_UNROLL;                       // chunks in flight per thread
+constexpr int kChunksPerTile = kThreadsPerCta * kUnroll;   // 512 chunks
+constexpr uint32_t kTileBytes = 16u * kChunksPerTile;      // 8 KiB of destination per tile
 constexpr int kMaxInlineDescs = 64;  // descriptors that travel in the kernel parameter block
+static_assert(kChunksPerTile <= 2048, "TileRec::geom holds the chunk count in 12 bits");
 
 // Device-side descriptor: mod_desc plus the index of the entry's first tile (32 bytes).
 struct __align__(16) DevDesc {
@@ -26,20 +29,25 @@ struct __align__(16) DevDesc {
     uint32_t len;
     int32_t key;
     uint32_t first_tile;
+    uint32_t neg_state;  // modlcg::key_to_neg_state(key), filled on the host (no division on the device)
+};
+
+// One record per tile, written once by the plan kernel and read (one 32-byte broadcast load) by
+// the CTA that owns the tile: everything it needs to start streaming, so the hot kernel does no
+// search, no division and no table walk.
+struct __align__(16) TileRec {
+    int64_t src_rel;   // source byte (relative to the src base) that pairs with byte 0 of the tile's chunk 0
+    int64_t dst_rel;   // destination byte (relative to the dst base) of chunk 0; base + dst_rel is 16-byte aligned
+    uint32_t state;    // negated LCG state just before byte 0 of chunk 0
+    uint32_t geom;     // bits 0-11: chunks in the tile; 12-15: first valid byte of chunk 0; 16-20: valid bytes of the last chunk
+    uint32_t entry;    // descriptor index (diagnostics)
     uint32_t pad;
 };
 
-// One record per tile, written once by the plan kernel and read (one 32-byte load, prefetched a
-// tile ahead) by the batched kernel: everything a warp needs to start streaming, so the hot kernel
-// does no search, no division and no table walk.
-struct __align__(16) TileRec {
-    uint64_t src_off;  // of the ENTRY this tile belongs to
-    uint64_t dst_off;
-    uint32_t len;      // entry length
-    uint32_t state;    // negated LCG state just before byte (16 * c_begin - h0) of the entry
-    uint32_t tin;      // tile index inside the entry (c_begin = tin * kChunksPerTile)
-    uint32_t pad;
-};
+__host__ __device__ inline uint32_t pack_geom(uint32_t n_valid, uint32_t head, uint32_t tail)
+{
+    return n_valid | (head << 12) | (tail << 16);
+}
 
 struct InlineDescs {
     DevDesc d[kMaxInlineDescs];
@@ -51,7 +59,6 @@ struct BatchArgs {
     const TileRec* tiles;  // HBM tile records (nullptr in inline mode)
     uint32_t n_tiles;
     uint32_t tiles_per_entry;  // inline mode: entry = tile / tiles_per_entry
-    uint32_t rounds_per_tile = kIters;  // inline mode: tile length in rounds of 32 chunks (a divisor of kIters)
     // 16-byte granules of the source may be loaded whole only inside [src_lo16, src_hi16).
     uint64_t src_lo16;
     uint64_t src_hi16;
@@ -60,18 +67,15 @@ struct BatchArgs {
 
 // Number of tiles an entry of `len` bytes occupies when its first destination byte sits at
 // (address & 15) == h0.
-__host__ __device__ inline uint32_t tiles_for_entry(uint32_t h0, uint32_t len,
-                                                    uint32_t chunks_per_tile = (uint32_t)kChunksPerTile)
+__host__ __device__ inline uint32_t tiles_for_entry(uint32_t h0, uint32_t len)
 {
     if (len == 0)
         return 0;
     const uint64_t chunks = ((uint64_t)h0 + len + 15u) >> 4;
-    return (uint32_t)((chunks + chunks_per_tile - 1) / chunks_per_tile);
+    return (uint32_t)((chunks + (uint32_t)kChunksPerTile - 1) / (uint32_t)kChunksPerTile);
 }
 
 cudaError_t upload_tables();  // jump tables -> __constant__ / global memory of the current device
-// Persistent grid size for the current device (SM count x resident CTAs per SM), cached per device.
-cudaError_t persistent_grid(int* grid_out, bool inline_kernel);
 cudaError_t launch_batch(const BatchArgs& args, cudaStream_t stream);
 cudaError_t launch_batch_inline(const BatchArgs& args, const InlineDescs& descs, cudaStream_t stream);
 // Plan kernel: expands descriptors into per-tile records (binary search + jump-ahead per tile).

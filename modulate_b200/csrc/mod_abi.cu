@@ -1,7 +1,8 @@
-// mod_abi.cu -- the C ABI declared in include/modulate_b200.h: device binding, pinned / HBM
+// mod_abi.cu -- the C ABI declared in include/modulate_b200.h: per-device contexts, pinned / HBM
 // memory helpers, CEncryptionCycler::Cycle on host or device buffers, descriptor plans for CArk's
-// extract / build data movement, and the host-side shard planner.  No CPU compute path exists
-// here: every byte of keystream is produced by the kernels in cycle_kernels.cu.
+// extract / build data movement, the in-process multi-GPU entry points and the host-side shard
+// planner.  No CPU compute path exists here: every byte of keystream is produced by the kernels in
+// cycle_kernels.cu.
 #include "../../include/modulate_b200.h"
 
 #include <cuda_runtime.h>
@@ -13,9 +14,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cycle_kernels.cuh"
@@ -26,7 +29,7 @@ namespace {
 #ifndef MOD_PIPE_SLOTS
 #define MOD_PIPE_SLOTS 4
 #endif
-constexpr int kPipeSlots = MOD_PIPE_SLOTS;               // slices in flight on the host-pointer path
+constexpr int kPipeSlots = MOD_PIPE_SLOTS;  // slices / groups in flight on the host-pointer paths
 constexpr uint64_t kMaxPiece = 1ull << 30;  // a contiguous stream is cut into <= 1 GiB pieces
 constexpr int kMaxDevices = 64;
 
@@ -51,20 +54,29 @@ int fail(int code, const char* fmt, ...)
             return fail(MOD_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
-struct Context {
-    std::mutex mu;
-    bool tables_ready[kMaxDevices] = {};
+// No C++ exception may cross the extern "C" boundary (a C caller would std::terminate).
+#define MOD_ABI_BEGIN try {
+#define MOD_ABI_END(name)                                                                       \
+    }                                                                                           \
+    catch (const std::bad_alloc&) { return fail(MOD_ERR_NOMEM, name ": out of host memory"); }  \
+    catch (const std::exception& ex__) { return fail(MOD_ERR_ARG, name ": %s", ex__.what()); }  \
+    catch (...) { return fail(MOD_ERR_ARG, name ": unknown exception"); }
+
+// Everything the library owns on ONE GPU.  Contexts of different devices are independent: binding
+// another device never tears one down, and the sharded entry points drive several at once.
+struct DeviceCtx {
     int device = -1;
+    std::atomic<bool> ready{false};
+    std::mutex mu;  // the host-pointer paths share the workspaces below: one call at a time per device
     cudaStream_t pipe_stream[kPipeSlots] = {};
-    bool streams_ready = false;
-    int streams_device = -1;
-    // grow-only HBM workspaces of the host-pointer paths (owned by streams_device)
+    cudaEvent_t plan_ready = nullptr;
+    // grow-only HBM workspaces: slices of mod_cycle, source / destination windows of mod_cycle_batch
     void* slice_buf[kPipeSlots] = {};
-    uint64_t slice_bytes = 0;
-    void* ws_src = nullptr;
-    uint64_t ws_src_bytes = 0;
-    void* ws_dst = nullptr;
-    uint64_t ws_dst_bytes = 0;
+    uint64_t slice_bytes[kPipeSlots] = {};
+    void* slot_src[kPipeSlots] = {};
+    uint64_t slot_src_bytes[kPipeSlots] = {};
+    void* slot_dst[kPipeSlots] = {};
+    uint64_t slot_dst_bytes[kPipeSlots] = {};
     // plan scratch of the host-pointer batch path: pinned staging for descriptors, HBM descriptors + tiles
     void* h_descs = nullptr;
     uint64_t h_descs_bytes = 0;
@@ -72,10 +84,10 @@ struct Context {
     uint64_t ws_descs_bytes = 0;
     void* ws_tiles = nullptr;
     uint64_t ws_tiles_bytes = 0;
-    cudaEvent_t plan_ready = nullptr;
 };
 
-Context g_ctx;
+DeviceCtx g_dev[kMaxDevices];
+std::mutex g_init_mu;
 
 double now_ms()
 {
@@ -90,43 +102,63 @@ uint64_t env_u64(const char* name, uint64_t dflt)
     return strtoull(v, nullptr, 10);
 }
 
-void release_workspaces_locked()
+// Switch the calling thread to `device` for the lifetime of the guard.
+class DeviceGuard {
+public:
+    int enter(int device)
+    {
+        CUDA_TRY(cudaGetDevice(&prev_));
+        if (prev_ != device) {
+            CUDA_TRY(cudaSetDevice(device));
+            active_ = true;
+        }
+        return MOD_OK;
+    }
+    ~DeviceGuard()
+    {
+        if (active_)
+            cudaSetDevice(prev_);
+    }
+
+private:
+    int prev_ = -1;
+    bool active_ = false;
+};
+
+void release_ctx(DeviceCtx& c)  // current device == c.device
 {
+    auto drop = [](void*& p, uint64_t& n) {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    };
     for (int i = 0; i < kPipeSlots; ++i) {
-        if (g_ctx.slice_buf[i])
-            cudaFree(g_ctx.slice_buf[i]);
-        g_ctx.slice_buf[i] = nullptr;
+        drop(c.slice_buf[i], c.slice_bytes[i]);
+        drop(c.slot_src[i], c.slot_src_bytes[i]);
+        drop(c.slot_dst[i], c.slot_dst_bytes[i]);
     }
-    g_ctx.slice_bytes = 0;
-    if (g_ctx.ws_src)
-        cudaFree(g_ctx.ws_src);
-    if (g_ctx.ws_dst)
-        cudaFree(g_ctx.ws_dst);
-    g_ctx.ws_src = g_ctx.ws_dst = nullptr;
-    g_ctx.ws_src_bytes = g_ctx.ws_dst_bytes = 0;
-    if (g_ctx.ws_descs)
-        cudaFree(g_ctx.ws_descs);
-    if (g_ctx.ws_tiles)
-        cudaFree(g_ctx.ws_tiles);
-    if (g_ctx.h_descs)
-        cudaFreeHost(g_ctx.h_descs);
-    g_ctx.ws_descs = g_ctx.ws_tiles = g_ctx.h_descs = nullptr;
-    g_ctx.ws_descs_bytes = g_ctx.ws_tiles_bytes = g_ctx.h_descs_bytes = 0;
-    if (g_ctx.plan_ready) {
-        cudaEventDestroy(g_ctx.plan_ready);
-        g_ctx.plan_ready = nullptr;
+    drop(c.ws_descs, c.ws_descs_bytes);
+    drop(c.ws_tiles, c.ws_tiles_bytes);
+    if (c.h_descs)
+        cudaFreeHost(c.h_descs);
+    c.h_descs = nullptr;
+    c.h_descs_bytes = 0;
+    if (c.plan_ready)
+        cudaEventDestroy(c.plan_ready);
+    c.plan_ready = nullptr;
+    for (int i = 0; i < kPipeSlots; ++i) {
+        if (c.pipe_stream[i])
+            cudaStreamDestroy(c.pipe_stream[i]);
+        c.pipe_stream[i] = nullptr;
     }
-    if (g_ctx.streams_ready) {
-        for (int i = 0; i < kPipeSlots; ++i)
-            cudaStreamDestroy(g_ctx.pipe_stream[i]);
-        g_ctx.streams_ready = false;
-    }
+    c.ready.store(false, std::memory_order_release);
 }
 
-// Bind + lazily prepare the current device.  Caller holds no lock.
-int ensure_ready(int device)
+// Bind (device >= 0) or keep (device < 0) the calling thread's CUDA device and return its context,
+// preparing it on first use: jump tables, pipeline streams.
+int acquire(int device, DeviceCtx** out)
 {
-    std::lock_guard<std::mutex> lock(g_ctx.mu);
     int count = 0;
     CUDA_TRY(cudaGetDeviceCount(&count));
     if (count <= 0)
@@ -140,33 +172,49 @@ int ensure_ready(int device)
     CUDA_TRY(cudaGetDevice(&cur));
     if (cur >= kMaxDevices)
         return fail(MOD_ERR_ARG, "device %d beyond the supported %d", cur, kMaxDevices);
-    if (!g_ctx.tables_ready[cur]) {
-        CUDA_TRY(modk::upload_tables());
-        g_ctx.tables_ready[cur] = true;
+    DeviceCtx& c = g_dev[cur];
+    if (!c.ready.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(g_init_mu);
+        if (!c.ready.load(std::memory_order_relaxed)) {
+            c.device = cur;
+            CUDA_TRY(modk::upload_tables());
+            for (int i = 0; i < kPipeSlots; ++i)
+                if (!c.pipe_stream[i])
+                    CUDA_TRY(cudaStreamCreateWithFlags(&c.pipe_stream[i], cudaStreamNonBlocking));
+            if (!c.plan_ready)
+                CUDA_TRY(cudaEventCreateWithFlags(&c.plan_ready, cudaEventDisableTiming));
+            c.ready.store(true, std::memory_order_release);
+        }
     }
-    if (g_ctx.streams_ready && g_ctx.streams_device != cur) {
-        cudaSetDevice(g_ctx.streams_device);
-        release_workspaces_locked();
-        cudaSetDevice(cur);
-    }
-    if (!g_ctx.streams_ready) {
-        for (int i = 0; i < kPipeSlots; ++i)
-            CUDA_TRY(cudaStreamCreateWithFlags(&g_ctx.pipe_stream[i], cudaStreamNonBlocking));
-        g_ctx.streams_ready = true;
-        g_ctx.streams_device = cur;
-    }
-    g_ctx.device = cur;
+    *out = &c;
     return MOD_OK;
 }
 
-bool is_device_pointer(const void* p)
+// Wait for everything the host-pointer paths have in flight on this device: called on every exit
+// of those paths, error exits included, because the copies reference the CALLER's buffers.
+cudaError_t drain(DeviceCtx& c)
+{
+    cudaError_t first = cudaSuccess;
+    for (int k = 0; k < kPipeSlots; ++k) {
+        const cudaError_t e = cudaStreamSynchronize(c.pipe_stream[k]);
+        if (first == cudaSuccess)
+            first = e;
+    }
+    return first;
+}
+
+bool pointer_device(const void* p, int* device)
 {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
-    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+    if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) {
+        *device = attr.device;
+        return true;
+    }
+    return false;
 }
 
 int grow(void** buf, uint64_t* have, uint64_t need)
@@ -182,96 +230,10 @@ int grow(void** buf, uint64_t* have, uint64_t need)
     cudaError_t e = cudaMalloc(buf, need);
     if (e != cudaSuccess) {
         cudaGetLastError();
+        *buf = nullptr;
         return fail(MOD_ERR_NOMEM, "cudaMalloc(%llu) failed: %s", (unsigned long long)need, cudaGetErrorString(e));
     }
     *have = need;
-    return MOD_OK;
-}
-
-// One launch (or a few, beyond 64 pieces) of the batched kernel over a contiguous stream.
-int launch_contiguous(const uint8_t* d_src, uint8_t* d_dst, uint64_t len, int32_t key, cudaStream_t stream)
-{
-    if (len == 0)
-        return MOD_OK;
-    const uint32_t h0 = (uint32_t)((uintptr_t)d_dst & 15u);
-    // piece size: <= 1 GiB, and large enough that one launch covers up to 64 pieces
-    uint64_t piece = kMaxPiece;
-    const uint64_t src_lo16 = ((uint64_t)(uintptr_t)d_src + 15u) & ~15ull;
-    const uint64_t src_hi16 = ((uint64_t)(uintptr_t)d_src + len) & ~15ull;
-    // short buffers use shorter tiles so that they still spread over the whole GPU: halve the tile
-    // until there is at least one tile per resident warp or a tile is a single round
-    uint32_t rounds = (uint32_t)modk::kIters;
-    {
-        int grid_cap = 0;
-        CUDA_TRY(modk::persistent_grid(&grid_cap, true));
-        const uint64_t want_tiles = (uint64_t)grid_cap * modk::kWarpsPerCta;
-        while (rounds > 1 && (len + 512ull * rounds - 1) / (512ull * rounds) < want_tiles)
-            rounds >>= 1;
-    }
-    const uint32_t cpt = 32u * rounds;  // chunks per tile
-    const uint32_t tpe = modk::tiles_for_entry(h0, (uint32_t)piece, cpt);
-    uint64_t done = 0;
-    uint32_t k0 = modlcg::key_residue(key);
-    while (done < len) {
-        modk::InlineDescs in;
-        modk::BatchArgs args;
-        uint32_t n = 0, tiles = 0;
-        const uint64_t group_base = done;
-        while (done < len && n < (uint32_t)modk::kMaxInlineDescs) {
-            const uint64_t this_len = std::min(piece, len - done);
-            modk::DevDesc& d = in.d[n];
-            d.src_off = done - group_base;
-            d.dst_off = done - group_base;
-            d.len = (uint32_t)this_len;
-            d.key = (int32_t)modlcg::mulmod(k0, modlcg::pow_a(done));
-            d.first_tile = n * tpe;
-            d.pad = 0;
-            tiles = n * tpe + modk::tiles_for_entry(h0, (uint32_t)this_len, cpt);
-            done += this_len;
-            ++n;
-        }
-        args.src = d_src + group_base;
-        args.dst = d_dst + group_base;
-        args.tiles = nullptr;
-        args.n_tiles = tiles;
-        args.tiles_per_entry = tpe;
-        args.rounds_per_tile = rounds;
-        args.src_lo16 = src_lo16;
-        args.src_hi16 = src_hi16;
-        CUDA_TRY(modk::launch_batch_inline(args, in, stream));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-    }
-    return MOD_OK;
-}
-
-// Validate descriptors against the buffer sizes and expand them into device descriptors with their
-// first-tile prefix.  Shared by mod_plan_create and the host-pointer batch path.
-int expand_descs(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint64_t dst_bytes, uint32_t dst_align,
-                 modk::DevDesc* out, uint64_t* tiles_out, uint64_t* payload_out)
-{
-    uint64_t tiles = 0, payload = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        const mod_desc& d = descs[i];
-        if (d.src_off > src_bytes || (uint64_t)d.len > src_bytes - d.src_off)
-            return fail(MOD_ERR_ARG, "descriptor %llu: source range [%llu, +%u) leaves the %llu-byte buffer",
-                        (unsigned long long)i, (unsigned long long)d.src_off, d.len, (unsigned long long)src_bytes);
-        if (d.dst_off > dst_bytes || (uint64_t)d.len > dst_bytes - d.dst_off)
-            return fail(MOD_ERR_ARG, "descriptor %llu: destination range [%llu, +%u) leaves the %llu-byte buffer",
-                        (unsigned long long)i, (unsigned long long)d.dst_off, d.len, (unsigned long long)dst_bytes);
-        modk::DevDesc& o = out[i];
-        o.src_off = d.src_off;
-        o.dst_off = d.dst_off;
-        o.len = d.len;
-        o.key = d.key;
-        o.first_tile = (uint32_t)tiles;
-        o.pad = 0;
-        tiles += modk::tiles_for_entry((uint32_t)((dst_align + d.dst_off) & 15u), d.len);
-        payload += d.len;
-        if (tiles >= 0xFFFFFFFFull)
-            return fail(MOD_ERR_ARG, "batch too large (tile count overflows 32 bits)");
-    }
-    *tiles_out = tiles;
-    *payload_out = payload;
     return MOD_OK;
 }
 
@@ -285,12 +247,496 @@ int grow_pinned(void** buf, uint64_t* have, uint64_t need)
         *have = 0;
     }
     need = (need + 4095) & ~4095ull;
-    cudaError_t e = cudaHostAlloc(buf, need, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(buf, need, cudaHostAllocPortable);
     if (e != cudaSuccess) {
         cudaGetLastError();
+        *buf = nullptr;
         return fail(MOD_ERR_NOMEM, "cudaHostAlloc(%llu) failed: %s", (unsigned long long)need, cudaGetErrorString(e));
     }
     *have = need;
+    return MOD_OK;
+}
+
+// One launch (or a few, beyond 64 pieces) of the batched kernel over a contiguous stream.
+int launch_contiguous(const uint8_t* d_src, uint8_t* d_dst, uint64_t len, int32_t key, cudaStream_t stream)
+{
+    if (len == 0)
+        return MOD_OK;
+    const uint32_t h0 = (uint32_t)((uintptr_t)d_dst & 15u);
+    const uint64_t piece = kMaxPiece;
+    const uint64_t src_lo16 = ((uint64_t)(uintptr_t)d_src + 15u) & ~15ull;
+    const uint64_t src_hi16 = ((uint64_t)(uintptr_t)d_src + len) & ~15ull;
+    const uint32_t tpe = modk::tiles_for_entry(h0, (uint32_t)piece);
+    uint64_t done = 0;
+    const uint32_t k0 = modlcg::key_residue(key);
+    while (done < len) {
+        modk::InlineDescs in;
+        modk::BatchArgs args;
+        uint32_t n = 0, tiles = 0;
+        const uint64_t group_base = done;
+        while (done < len && n < (uint32_t)modk::kMaxInlineDescs) {
+            const uint64_t this_len = std::min(piece, len - done);
+            modk::DevDesc& d = in.d[n];
+            d.src_off = done - group_base;
+            d.dst_off = done - group_base;
+            d.len = (uint32_t)this_len;
+            d.key = (int32_t)modlcg::mulmod(k0, modlcg::pow_a(done));
+            d.first_tile = n * tpe;
+            d.neg_state = modlcg::key_to_neg_state(d.key);
+            tiles = n * tpe + modk::tiles_for_entry(h0, (uint32_t)this_len);
+            done += this_len;
+            ++n;
+        }
+        args.src = d_src + group_base;
+        args.dst = d_dst + group_base;
+        args.tiles = nullptr;
+        args.n_tiles = tiles;
+        args.tiles_per_entry = tpe;
+        args.src_lo16 = src_lo16;
+        args.src_hi16 = src_hi16;
+        CUDA_TRY(modk::launch_batch_inline(args, in, stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return MOD_OK;
+}
+
+// CEncryptionCycler::Cycle on a HOST buffer: slices travel H2D -> kernel -> D2H on kPipeSlots streams
+// so that the upload of slice i+1, the kernel of slice i and the download of slice i-1 overlap.
+int cycle_host(DeviceCtx& c, uint8_t* host, uint64_t len, int32_t key)
+{
+    std::lock_guard<std::mutex> lock(c.mu);
+    uint64_t slice = env_u64("MOD_SLICE_BYTES", 16ull << 20);
+    slice = std::max<uint64_t>(4096, slice & ~4095ull);
+    if (len < slice * 2)  // small buffers: still use several slots so both directions overlap
+        slice = std::max<uint64_t>(4096, ((len / kPipeSlots) + 4095) & ~4095ull);
+    const int slots = (int)std::min<uint64_t>(kPipeSlots, (len + slice - 1) / slice);
+    for (int i = 0; i < slots; ++i) {
+        const int rc = grow(&c.slice_buf[i], &c.slice_bytes[i], slice);
+        if (rc != MOD_OK)
+            return rc;
+    }
+    const uint32_t k0 = modlcg::key_residue(key);
+    int rc = MOD_OK;
+    cudaError_t e = cudaSuccess;
+    uint64_t pos = 0;
+    for (uint64_t i = 0; pos < len && rc == MOD_OK && e == cudaSuccess; ++i) {
+        const int slot = (int)(i % kPipeSlots);
+        const uint64_t n = std::min(slice, len - pos);
+        cudaStream_t s = c.pipe_stream[slot];
+        uint8_t* d = (uint8_t*)c.slice_buf[slot];
+        e = cudaMemcpyAsync(d, host + pos, n, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess)
+            break;
+        rc = launch_contiguous(d, d, n, (int32_t)modlcg::mulmod(k0, modlcg::pow_a(pos)), s);
+        if (rc != MOD_OK)
+            break;
+        e = cudaMemcpyAsync(host + pos, d, n, cudaMemcpyDeviceToHost, s);
+        pos += n;
+    }
+    const cudaError_t ed = drain(c);  // also on failure: the copies in flight touch the caller's buffer
+    if (rc != MOD_OK)
+        return rc;
+    if (e == cudaSuccess)
+        e = ed;
+    if (e != cudaSuccess)
+        return fail(MOD_ERR_CUDA, "mod_cycle: %s", cudaGetErrorString(e));
+    return MOD_OK;
+}
+
+int validate_descs(const char* who, const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint64_t dst_bytes)
+{
+    for (uint64_t i = 0; i < n; ++i) {
+        const mod_desc& d = descs[i];
+        if (d.src_off > src_bytes || (uint64_t)d.len > src_bytes - d.src_off)
+            return fail(MOD_ERR_ARG, "%s: descriptor %llu: source range [%llu, +%u) leaves the %llu-byte buffer", who,
+                        (unsigned long long)i, (unsigned long long)d.src_off, d.len, (unsigned long long)src_bytes);
+        if (d.dst_off > dst_bytes || (uint64_t)d.len > dst_bytes - d.dst_off)
+            return fail(MOD_ERR_ARG, "%s: descriptor %llu: destination range [%llu, +%u) leaves the %llu-byte buffer", who,
+                        (unsigned long long)i, (unsigned long long)d.dst_off, d.len, (unsigned long long)dst_bytes);
+    }
+    return MOD_OK;
+}
+
+// Expand (already validated) descriptors into device descriptors with their first-tile prefix.
+int expand_descs(const mod_desc* descs, uint64_t n, uint32_t dst_align, modk::DevDesc* out, uint64_t* tiles_out,
+                 uint64_t* payload_out)
+{
+    uint64_t tiles = 0, payload = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const mod_desc& d = descs[i];
+        modk::DevDesc& o = out[i];
+        o.src_off = d.src_off;
+        o.dst_off = d.dst_off;
+        o.len = d.len;
+        o.key = d.key;
+        o.first_tile = (uint32_t)tiles;
+        o.neg_state = modlcg::key_to_neg_state(d.key);
+        tiles += modk::tiles_for_entry((uint32_t)((dst_align + d.dst_off) & 15u), d.len);
+        payload += d.len;
+        if (tiles >= 0xFFFFFFFFull)
+            return fail(MOD_ERR_ARG, "batch too large (tile count overflows 32 bits)");
+    }
+    *tiles_out = tiles;
+    *payload_out = payload;
+    return MOD_OK;
+}
+
+// ---- mod_cycle_batch on HOST buffers -------------------------------------------------------------------
+//
+// The entries are streamed in GROUPS of consecutive descriptors (~MOD_GROUP_BYTES of payload each;
+// entries larger than that are first cut into pieces with jumped keys).  One plan (descriptors ->
+// tile records) is built for the whole call, asynchronously on pipe stream 0.  Group g then uploads
+// the source WINDOW its entries span into slot g % kPipeSlots, runs the batched kernel over its tile
+// sub-range against the slot's two window buffers, and downloads the destination runs it covers --
+// so the upload of one group, the kernel of another and the download of a third overlap, and HBM
+// use is O(slots x group), not O(archive).  Only bytes covered by descriptors are written back, so
+// untouched bytes of dst survive exactly like with the reference's per-entry fwrite / fread.
+struct Group {
+    uint64_t e0, e1;      // descriptor range
+    uint32_t t0, t1;      // tile range
+    uint64_t s_lo, s_hi;  // source window
+    uint64_t d_lo, d_hi;  // destination window
+};
+
+int batch_host(DeviceCtx& c, const mod_desc* user_descs, uint64_t user_n, const uint8_t* src, uint64_t src_bytes,
+               uint8_t* dst, uint64_t dst_bytes)
+{
+    const bool trace = env_u64("MOD_TRACE", 0) != 0;
+    const double t_begin = now_ms();
+    int rc = validate_descs("mod_cycle_batch", user_descs, user_n, src_bytes, dst_bytes);
+    if (rc != MOD_OK)
+        return rc;
+
+    // entries larger than a group are cut at 16-byte destination boundaries; the pieces continue
+    // the entry's keystream through jumped keys
+    const uint64_t group_bytes = std::max<uint64_t>(1 << 20, env_u64("MOD_GROUP_BYTES", 16ull << 20)) & ~15ull;
+    std::vector<mod_desc> cut;
+    bool any_big = false;
+    for (uint64_t i = 0; i < user_n && !any_big; ++i)
+        any_big = user_descs[i].len > group_bytes + (group_bytes >> 1);
+    if (any_big) {
+        cut.reserve(user_n + 64);
+        for (uint64_t i = 0; i < user_n; ++i) {
+            const mod_desc& d = user_descs[i];
+            if (d.len <= group_bytes + (group_bytes >> 1)) {
+                cut.push_back(d);
+                continue;
+            }
+            const uint32_t k0 = modlcg::key_residue(d.key);
+            uint64_t pos = 0;
+            while (pos < d.len) {
+                uint64_t take = std::min<uint64_t>(group_bytes - ((d.dst_off + pos) & 15u), d.len - pos);
+                if (d.len - pos - take < (group_bytes >> 1))
+                    take = d.len - pos;  // no short tail piece
+                cut.push_back(mod_desc{d.src_off + pos, d.dst_off + pos, (uint32_t)take,
+                                       (int32_t)modlcg::mulmod(k0, modlcg::pow_a(pos))});
+                pos += take;
+            }
+        }
+    }
+    const mod_desc* descs = any_big ? cut.data() : user_descs;
+    const uint64_t n = any_big ? cut.size() : user_n;
+    if (n >= 0xFFFFFFFFull)
+        return fail(MOD_ERR_ARG, "mod_cycle_batch: too many descriptors (%llu)", (unsigned long long)n);
+
+    std::lock_guard<std::mutex> lock(c.mu);
+    if ((rc = grow_pinned(&c.h_descs, &c.h_descs_bytes, n * sizeof(modk::DevDesc))) != MOD_OK)
+        return rc;
+    uint64_t plan_tiles = 0, plan_payload = 0;
+    if ((rc = expand_descs(descs, n, 0, (modk::DevDesc*)c.h_descs, &plan_tiles, &plan_payload)) != MOD_OK)
+        return rc;
+    if (plan_tiles == 0)
+        return MOD_OK;
+    if ((rc = grow(&c.ws_descs, &c.ws_descs_bytes, n * sizeof(modk::DevDesc))) != MOD_OK)
+        return rc;
+    if ((rc = grow(&c.ws_tiles, &c.ws_tiles_bytes, plan_tiles * sizeof(modk::TileRec))) != MOD_OK)
+        return rc;
+
+    // groups of consecutive descriptors and the windows they span
+    std::vector<Group> groups;
+    auto whole = [&]() {
+        Group all{0, n, 0, (uint32_t)plan_tiles, UINT64_MAX, 0, UINT64_MAX, 0};
+        for (uint64_t i = 0; i < n; ++i) {
+            if (!descs[i].len)
+                continue;
+            all.s_lo = std::min(all.s_lo, descs[i].src_off);
+            all.s_hi = std::max(all.s_hi, descs[i].src_off + descs[i].len);
+            all.d_lo = std::min(all.d_lo, descs[i].dst_off);
+            all.d_hi = std::max(all.d_hi, descs[i].dst_off + descs[i].len);
+        }
+        groups.assign(1, all);
+    };
+    {
+        Group g{0, 0, 0, 0, UINT64_MAX, 0, UINT64_MAX, 0};
+        uint64_t acc = 0;
+        uint32_t tile = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            const mod_desc& d = descs[i];
+            if (d.len) {
+                g.s_lo = std::min(g.s_lo, d.src_off);
+                g.s_hi = std::max(g.s_hi, d.src_off + d.len);
+                g.d_lo = std::min(g.d_lo, d.dst_off);
+                g.d_hi = std::max(g.d_hi, d.dst_off + d.len);
+            }
+            acc += d.len;
+            tile += modk::tiles_for_entry((uint32_t)(d.dst_off & 15u), d.len);
+            if (acc >= group_bytes || i + 1 == n) {
+                g.e1 = i + 1;
+                g.t1 = tile;
+                if (g.t1 > g.t0)
+                    groups.push_back(g);
+                g = Group{i + 1, 0, tile, 0, UINT64_MAX, 0, UINT64_MAX, 0};
+                acc = 0;
+            }
+        }
+    }
+    // If the entries are not laid out in order the windows overlap heavily and per-group copies would
+    // move the buffers many times: one group over the full extents then.
+    {
+        uint64_t s_sum = 0, d_sum = 0;
+        for (const Group& g : groups) {
+            s_sum += g.s_hi - g.s_lo;
+            d_sum += g.d_hi - g.d_lo;
+        }
+        if (s_sum > src_bytes + src_bytes / 4 + (1 << 20) || d_sum > dst_bytes + dst_bytes / 4 + (1 << 20))
+            whole();
+    }
+
+    // Destination runs (maximal intervals downloaded with one copy) per group.  Two entries that are
+    // neighbours in the GLOBAL destination order and less than 16 bytes apart (alignment padding) are
+    // bridged into one run; the host bytes of such a gap are saved first and put back after the
+    // download, so every byte not covered by a descriptor keeps its value.  A batch whose destination
+    // is full of larger holes (more than 64 runs in a group) is handled exactly but without
+    // pipelining: its whole destination extent makes a round trip through HBM.
+    std::vector<uint32_t> rank(n, 0);   // position of each non-empty entry in global dst order
+    std::vector<uint8_t> bridge_after;  // by rank: the gap to the next entry may be bridged
+    {
+        std::vector<uint32_t> order;
+        order.reserve(n);
+        bool monotone = true;
+        uint64_t last = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            if (!descs[i].len)
+                continue;
+            if (descs[i].dst_off < last)
+                monotone = false;
+            last = descs[i].dst_off;
+            order.push_back((uint32_t)i);
+        }
+        if (!monotone)
+            std::sort(order.begin(), order.end(),
+                      [&](uint32_t a, uint32_t b) { return descs[a].dst_off < descs[b].dst_off; });
+        bridge_after.assign(order.size(), 0);
+        for (size_t r = 0; r < order.size(); ++r) {
+            rank[order[r]] = (uint32_t)r;
+            if (r + 1 < order.size()) {
+                const uint64_t end = descs[order[r]].dst_off + descs[order[r]].len;
+                const uint64_t nxt = descs[order[r + 1]].dst_off;
+                bridge_after[r] = (nxt >= end && nxt - end < 16) ? 1 : 0;
+            }
+        }
+    }
+    struct Gap {
+        uint64_t off;
+        uint32_t len;
+        uint8_t bytes[15];
+    };
+    std::vector<Gap> gaps;
+    std::vector<uint32_t> members;
+    auto merged_runs = [&](const Group& g, std::vector<std::pair<uint64_t, uint64_t>>& runs, bool save_gaps) {
+        runs.clear();
+        members.clear();
+        for (uint64_t i = g.e0; i < g.e1; ++i)
+            if (descs[i].len)
+                members.push_back((uint32_t)i);
+        std::sort(members.begin(), members.end(), [&](uint32_t a, uint32_t b) { return rank[a] < rank[b]; });
+        uint32_t prev_rank = 0;
+        for (uint32_t idx : members) {
+            const uint64_t b0 = descs[idx].dst_off, b1 = b0 + descs[idx].len;
+            const bool adjacent = !runs.empty() && rank[idx] == prev_rank + 1;
+            if (adjacent && b0 <= runs.back().second) {
+                runs.back().second = std::max(runs.back().second, b1);
+            } else if (adjacent && bridge_after[prev_rank] && b0 - runs.back().second < 16) {
+                if (save_gaps && b0 > runs.back().second) {
+                    Gap gap;
+                    gap.off = runs.back().second;
+                    gap.len = (uint32_t)(b0 - runs.back().second);
+                    std::memcpy(gap.bytes, dst + gap.off, gap.len);
+                    gaps.push_back(gap);
+                }
+                runs.back().second = b1;
+            } else {
+                runs.emplace_back(b0, b1);
+            }
+            prev_rank = rank[idx];
+        }
+    };
+    std::vector<std::pair<uint64_t, uint64_t>> runs;
+    bool holes = false;
+    for (const Group& g : groups) {
+        merged_runs(g, runs, false);
+        if (runs.size() > 64) {
+            holes = true;
+            break;
+        }
+    }
+    if (holes)
+        whole();
+
+    // slot buffers: the source window keeps its (offset & 15) phase and the destination window starts
+    // at a 16-byte boundary of the destination space, so host co-alignment survives on the device
+    const int slots = (int)std::min<size_t>(kPipeSlots, groups.size());
+    {
+        uint64_t s_need = 0, d_need = 0;
+        for (const Group& g : groups) {
+            s_need = std::max<uint64_t>(s_need, (g.s_lo & 15u) + (g.s_hi - g.s_lo));
+            d_need = std::max<uint64_t>(d_need, g.d_hi - (g.d_lo & ~15ull));
+        }
+        for (int k = 0; k < slots; ++k) {
+            if ((rc = grow(&c.slot_src[k], &c.slot_src_bytes[k], s_need)) != MOD_OK)
+                return rc;
+            if ((rc = grow(&c.slot_dst[k], &c.slot_dst_bytes[k], d_need)) != MOD_OK)
+                return rc;
+        }
+    }
+
+    cudaError_t e = cudaMemcpyAsync(c.ws_descs, c.h_descs, n * sizeof(modk::DevDesc), cudaMemcpyHostToDevice, c.pipe_stream[0]);
+    if (e == cudaSuccess) {
+        e = modk::launch_build_tiles((const modk::DevDesc*)c.ws_descs, (uint32_t)n, 0, (modk::TileRec*)c.ws_tiles,
+                                     (uint32_t)plan_tiles, c.pipe_stream[0]);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    if (e == cudaSuccess)
+        e = cudaEventRecord(c.plan_ready, c.pipe_stream[0]);
+    const modk::TileRec* d_tiles = (const modk::TileRec*)c.ws_tiles;
+    const double t_plan = now_ms();
+
+    // test hook (tests/test_gpu_multidev.py): pretend the runtime failed at this group, with earlier
+    // groups still in flight, to exercise the drain-before-return path
+    const uint64_t fail_group = env_u64("MOD_TEST_FAIL_GROUP", UINT64_MAX);
+    for (size_t gi = 0; gi < groups.size() && e == cudaSuccess; ++gi) {
+        if (gi == fail_group) {
+            e = cudaErrorUnknown;
+            break;
+        }
+        const Group& g = groups[gi];
+        const int k = (int)(gi % (size_t)slots);
+        cudaStream_t s = c.pipe_stream[k];
+        uint8_t* win_src = (uint8_t*)c.slot_src[k] + (g.s_lo & 15u);  // holds source bytes [s_lo, s_hi)
+        uint8_t* win_dst = (uint8_t*)c.slot_dst[k];                    // holds destination bytes [d_lo16, d_hi)
+        const uint64_t d_lo16 = g.d_lo & ~15ull;
+        e = cudaMemcpyAsync(win_src, src + g.s_lo, g.s_hi - g.s_lo, cudaMemcpyHostToDevice, s);
+        if (e == cudaSuccess && holes)
+            e = cudaMemcpyAsync(win_dst, dst + d_lo16, g.d_hi - d_lo16, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess)
+            break;
+        if (!holes)
+            merged_runs(g, runs, true);
+        if (gi > 0 && gi < (size_t)slots) {  // first use of this stream: the plan must be complete
+            e = cudaStreamWaitEvent(s, c.plan_ready, 0);
+            if (e != cudaSuccess)
+                break;
+        }
+        modk::BatchArgs args;
+        args.src = win_src - g.s_lo;  // virtual bases: base + offset lands inside the window
+        args.dst = win_dst - d_lo16;
+        args.tiles = d_tiles + g.t0;
+        args.n_tiles = g.t1 - g.t0;
+        args.tiles_per_entry = 0;
+        args.src_lo16 = ((uint64_t)(uintptr_t)win_src + 15u) & ~15ull;
+        args.src_hi16 = ((uint64_t)(uintptr_t)win_src + (g.s_hi - g.s_lo)) & ~15ull;
+        e = modk::launch_batch(args, s);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (e != cudaSuccess)
+            break;
+        if (holes) {
+            e = cudaMemcpyAsync(dst + d_lo16, win_dst, g.d_hi - d_lo16, cudaMemcpyDeviceToHost, s);
+        } else {
+            for (const auto& r : runs) {
+                e = cudaMemcpyAsync(dst + r.first, win_dst + (r.first - d_lo16), r.second - r.first,
+                                    cudaMemcpyDeviceToHost, s);
+                if (e != cudaSuccess)
+                    break;
+            }
+        }
+    }
+    const double t_enq = now_ms();
+    const cudaError_t ed = drain(c);  // also on failure: the copies in flight touch the caller's buffers
+    if (e == cudaSuccess)
+        e = ed;
+    if (e == cudaSuccess)
+        for (const Gap& gap : gaps)  // put the padding bytes the bridged downloads ran over back
+            std::memcpy(dst + gap.off, gap.bytes, gap.len);
+    if (trace)
+        fprintf(stderr, "[mod] cycle_batch dev %d: plan %.2f ms, enqueue %zu groups %.2f ms, drain %.2f ms\n", c.device,
+                t_plan - t_begin, groups.size(), t_enq - t_plan, now_ms() - t_enq);
+    if (e != cudaSuccess)
+        return fail(MOD_ERR_CUDA, "mod_cycle_batch: %s", cudaGetErrorString(e));
+    return MOD_OK;
+}
+
+// ---- in-process multi-GPU: one host thread + stream set per selected device --------------------------------
+
+int selected_devices(uint64_t dev_mask, std::vector<int>& out)
+{
+    int count = 0;
+    CUDA_TRY(cudaGetDeviceCount(&count));
+    if (count <= 0)
+        return fail(MOD_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
+    for (int d = 0; d < count && d < kMaxDevices; ++d)
+        if (dev_mask == 0 || ((dev_mask >> d) & 1ull))
+            out.push_back(d);
+    if (out.empty())
+        return fail(MOD_ERR_ARG, "dev_mask 0x%llx selects none of the %d visible devices", (unsigned long long)dev_mask, count);
+    return MOD_OK;
+}
+
+// fn(rank, world, ctx) runs once per selected device, each on its own host thread bound to that
+// device; the first failure (by rank) is reported with its message.
+template <class F>
+int for_each_device(uint64_t dev_mask, F fn)
+{
+    std::vector<int> devs;
+    int rc = selected_devices(dev_mask, devs);
+    if (rc != MOD_OK)
+        return rc;
+    const int world = (int)devs.size();
+    std::vector<int> rcs((size_t)world, MOD_OK);
+    std::vector<std::string> errs((size_t)world);
+    auto body = [&](int r) {
+        try {
+            DeviceCtx* c = nullptr;
+            int my = acquire(devs[(size_t)r], &c);
+            if (my == MOD_OK)
+                my = fn(r, world, *c);
+            rcs[(size_t)r] = my;
+        } catch (const std::bad_alloc&) {
+            rcs[(size_t)r] = fail(MOD_ERR_NOMEM, "out of host memory");
+        } catch (...) {
+            rcs[(size_t)r] = fail(MOD_ERR_ARG, "unexpected exception");
+        }
+        if (rcs[(size_t)r] != MOD_OK)
+            errs[(size_t)r] = tl_error;
+    };
+    if (world == 1) {  // on the calling thread; acquire() binds the device, so put the caller's back afterwards
+        int prev = 0;
+        CUDA_TRY(cudaGetDevice(&prev));
+        body(0);
+        cudaSetDevice(prev);
+    } else {
+        std::vector<std::thread> threads;
+        threads.reserve((size_t)world);
+        for (int r = 0; r < world; ++r)
+            threads.emplace_back(body, r);
+        for (std::thread& t : threads)
+            t.join();
+    }
+    for (int r = 0; r < world; ++r) {
+        if (rcs[(size_t)r] != MOD_OK) {
+            tl_error = "device " + std::to_string(devs[(size_t)r]) + ": " + errs[(size_t)r];
+            return rcs[(size_t)r];
+        }
+    }
     return MOD_OK;
 }
 
@@ -305,6 +751,8 @@ struct mod_plan {
     uint64_t payload = 0;
     uint32_t n_tiles = 0;
     modk::TileRec* d_tiles = nullptr;
+    std::vector<mod_desc> descs;        // host copy: window validation, tile ranges
+    std::vector<uint32_t> first_tile;   // n + 1 entries
 };
 
 extern "C" {
@@ -326,16 +774,31 @@ int mod_device_count(void)
     return count;
 }
 
-int mod_init(int device) { return ensure_ready(device); }
+int mod_init(int device)
+{
+    DeviceCtx* c = nullptr;
+    return acquire(device, &c);
+}
 
 void mod_shutdown(void)
 {
-    std::lock_guard<std::mutex> lock(g_ctx.mu);
-    if (g_ctx.streams_ready) {
-        cudaSetDevice(g_ctx.streams_device);
+    std::lock_guard<std::mutex> init_lock(g_init_mu);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (int d = 0; d < kMaxDevices; ++d) {
+        DeviceCtx& c = g_dev[d];
+        if (!c.ready.load(std::memory_order_acquire))
+            continue;
+        std::lock_guard<std::mutex> lock(c.mu);
+        if (cudaSetDevice(d) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
         cudaDeviceSynchronize();
+        release_ctx(c);
     }
-    release_workspaces_locked();
+    if (prev >= 0)
+        cudaSetDevice(prev);
 }
 
 /* ---- memory helpers ------------------------------------------------------------------------ */
@@ -343,7 +806,7 @@ void mod_shutdown(void)
 void* mod_host_alloc(uint64_t bytes)
 {
     void* p = nullptr;
-    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
     if (e != cudaSuccess) {
         cudaGetLastError();
         fail(MOD_ERR_NOMEM, "cudaHostAlloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
@@ -398,6 +861,29 @@ int mod_stream_sync(void* stream)
     return MOD_OK;
 }
 
+void* mod_stream_create(void)
+{
+    DeviceCtx* c = nullptr;
+    if (acquire(-1, &c) != MOD_OK)
+        return nullptr;
+    cudaStream_t s = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail(MOD_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+        return nullptr;
+    }
+    return (void*)s;
+}
+
+int mod_stream_destroy(void* stream)
+{
+    if (!stream)
+        return MOD_OK;
+    CUDA_TRY(cudaStreamDestroy((cudaStream_t)stream));
+    return MOD_OK;
+}
+
 /* ---- CEncryptionCycler::Cycle ---------------------------------------------------------------- */
 
 int32_t mod_key_jump(int32_t key, uint64_t pos)
@@ -411,7 +897,8 @@ int mod_cycle_device(const void* d_src, void* d_dst, uint64_t len, int32_t key, 
         return MOD_OK;
     if (!d_src || !d_dst)
         return fail(MOD_ERR_ARG, "mod_cycle_device: null pointer");
-    int rc = ensure_ready(-1);
+    DeviceCtx* c = nullptr;
+    int rc = acquire(-1, &c);
     if (rc != MOD_OK)
         return rc;
     return launch_contiguous((const uint8_t*)d_src, (uint8_t*)d_dst, len, key, (cudaStream_t)stream);
@@ -419,58 +906,52 @@ int mod_cycle_device(const void* d_src, void* d_dst, uint64_t len, int32_t key, 
 
 int mod_cycle(void* data, uint64_t len, int32_t key)
 {
+    MOD_ABI_BEGIN
     if (len == 0)
         return MOD_OK;
     if (!data)
         return fail(MOD_ERR_ARG, "mod_cycle: null pointer");
-    int rc = ensure_ready(-1);
-    if (rc != MOD_OK)
-        return rc;
-
-    if (is_device_pointer(data)) {
-        rc = launch_contiguous((const uint8_t*)data, (uint8_t*)data, len, key, nullptr);
+    int ptr_dev = -1;
+    if (pointer_device(data, &ptr_dev)) {  // resident buffer: cycle it where it lives
+        DeviceGuard guard;
+        int rc = guard.enter(ptr_dev);
         if (rc != MOD_OK)
+            return rc;
+        DeviceCtx* c = nullptr;
+        if ((rc = acquire(-1, &c)) != MOD_OK)
+            return rc;
+        if ((rc = launch_contiguous((const uint8_t*)data, (uint8_t*)data, len, key, nullptr)) != MOD_OK)
             return rc;
         CUDA_TRY(cudaStreamSynchronize(nullptr));
         return MOD_OK;
     }
+    DeviceCtx* c = nullptr;
+    int rc = acquire(-1, &c);
+    if (rc != MOD_OK)
+        return rc;
+    return cycle_host(*c, (uint8_t*)data, len, key);
+    MOD_ABI_END("mod_cycle")
+}
 
-    // Host buffer: slices travel H2D -> kernel -> D2H on kPipeSlots streams so that the upload of
-    // slice i+1, the kernel of slice i and the download of slice i-1 overlap (two copy engines).
-    std::lock_guard<std::mutex> lock(g_ctx.mu);
-    uint64_t slice = env_u64("MOD_SLICE_BYTES", 16ull << 20);
-    slice = std::max<uint64_t>(4096, slice & ~4095ull);
-    if (len < slice * 2)  // small buffers: still use several slots so both directions overlap
-        slice = std::max<uint64_t>(4096, ((len / kPipeSlots) + 4095) & ~4095ull);
-    if (g_ctx.slice_bytes < slice) {
-        for (int i = 0; i < kPipeSlots; ++i) {
-            uint64_t have = g_ctx.slice_bytes;
-            rc = grow(&g_ctx.slice_buf[i], &have, slice);
-            if (rc != MOD_OK) {
-                g_ctx.slice_bytes = 0;
-                return rc;
-            }
-        }
-        g_ctx.slice_bytes = slice;
-    }
+int mod_cycle_sharded(void* data, uint64_t len, int32_t key, uint64_t dev_mask)
+{
+    MOD_ABI_BEGIN
+    if (len == 0)
+        return MOD_OK;
+    if (!data)
+        return fail(MOD_ERR_ARG, "mod_cycle_sharded: null pointer");
+    int ptr_dev = -1;
+    if (pointer_device(data, &ptr_dev))
+        return fail(MOD_ERR_ARG, "mod_cycle_sharded: `data` must be a host buffer (a device buffer lives on one GPU: use mod_cycle)");
     uint8_t* host = (uint8_t*)data;
-    const uint32_t k0 = modlcg::key_residue(key);
-    uint64_t pos = 0;
-    for (uint64_t i = 0; pos < len; ++i) {
-        const int slot = (int)(i % kPipeSlots);
-        const uint64_t n = std::min(slice, len - pos);
-        cudaStream_t s = g_ctx.pipe_stream[slot];
-        uint8_t* d = (uint8_t*)g_ctx.slice_buf[slot];
-        CUDA_TRY(cudaMemcpyAsync(d, host + pos, n, cudaMemcpyHostToDevice, s));
-        rc = launch_contiguous(d, d, n, (int32_t)modlcg::mulmod(k0, modlcg::pow_a(pos)), s);
-        if (rc != MOD_OK)
+    return for_each_device(dev_mask, [=](int rank, int world, DeviceCtx& c) -> int {
+        uint64_t b = 0, e = 0;
+        int rc = mod_shard_range(len, rank, world, &b, &e);
+        if (rc != MOD_OK || e <= b)
             return rc;
-        CUDA_TRY(cudaMemcpyAsync(host + pos, d, n, cudaMemcpyDeviceToHost, s));
-        pos += n;
-    }
-    for (int i = 0; i < kPipeSlots; ++i)
-        CUDA_TRY(cudaStreamSynchronize(g_ctx.pipe_stream[i]));
-    return MOD_OK;
+        return cycle_host(c, host + b, e - b, mod_key_jump(key, b));
+    });
+    MOD_ABI_END("mod_cycle_sharded")
 }
 
 /* ---- descriptor plans -------------------------------------------------------------------------- */
@@ -478,6 +959,7 @@ int mod_cycle(void* data, uint64_t len, int32_t key)
 int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint64_t dst_bytes,
                     uint32_t dst_align, mod_plan** out)
 {
+    MOD_ABI_BEGIN
     if (!out)
         return fail(MOD_ERR_ARG, "mod_plan_create: out is null");
     *out = nullptr;
@@ -487,24 +969,20 @@ int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint6
         return fail(MOD_ERR_ARG, "mod_plan_create: too many descriptors (%llu)", (unsigned long long)n);
     if (dst_align > 15)
         return fail(MOD_ERR_ARG, "mod_plan_create: dst_align must be < 16");
-    int rc = ensure_ready(-1);
+    DeviceCtx* c = nullptr;
+    int rc = acquire(-1, &c);
     if (rc != MOD_OK)
         return rc;
-
-    std::vector<modk::DevDesc> host;
-    try {
-        host.resize(n);
-    } catch (const std::bad_alloc&) {
-        return fail(MOD_ERR_NOMEM, "mod_plan_create: host allocation of %llu descriptors failed", (unsigned long long)n);
-    }
-    uint64_t tiles = 0, payload = 0;
-    if ((rc = expand_descs(descs, n, src_bytes, dst_bytes, dst_align, host.data(), &tiles, &payload)) != MOD_OK)
+    if ((rc = validate_descs("mod_plan_create", descs, n, src_bytes, dst_bytes)) != MOD_OK)
         return rc;
 
-    mod_plan* p = new (std::nothrow) mod_plan();
-    if (!p)
-        return fail(MOD_ERR_NOMEM, "mod_plan_create: out of host memory");
-    p->device = g_ctx.device;
+    std::vector<modk::DevDesc> host(n);
+    uint64_t tiles = 0, payload = 0;
+    if ((rc = expand_descs(descs, n, dst_align, host.data(), &tiles, &payload)) != MOD_OK)
+        return rc;
+
+    mod_plan* p = new mod_plan();
+    p->device = c->device;
     p->n = n;
     p->src_bytes = src_bytes;
     p->dst_bytes = dst_bytes;
@@ -517,6 +995,16 @@ int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint6
         if (p->d_tiles) cudaFree(p->d_tiles);
         delete p;
     };
+    try {
+        p->descs.assign(descs, descs + n);
+        p->first_tile.resize(n + 1);
+        for (uint64_t i = 0; i < n; ++i)
+            p->first_tile[i] = host[i].first_tile;
+        p->first_tile[n] = (uint32_t)tiles;
+    } catch (...) {
+        cleanup();
+        throw;
+    }
     if (n && tiles) {
         cudaError_t e = cudaMalloc((void**)&d_descs, n * sizeof(modk::DevDesc));
         if (e == cudaSuccess)
@@ -542,20 +1030,47 @@ int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint6
     }
     *out = p;
     return MOD_OK;
+    MOD_ABI_END("mod_plan_create")
 }
 
 int mod_plan_destroy(mod_plan* plan)
 {
     if (!plan)
         return MOD_OK;
-    if (plan->d_tiles)
+    if (plan->d_tiles) {
+        DeviceGuard guard;
+        guard.enter(plan->device);
         cudaFree(plan->d_tiles);
+    }
     delete plan;
     return MOD_OK;
 }
 
 uint64_t mod_plan_payload_bytes(const mod_plan* plan) { return plan ? plan->payload : 0; }
 uint64_t mod_plan_num_tiles(const mod_plan* plan) { return plan ? plan->n_tiles : 0; }
+
+int mod_plan_tile_range(const mod_plan* plan, uint64_t entry_begin, uint64_t entry_end, uint64_t* tile_begin,
+                        uint64_t* tile_end)
+{
+    if (!plan || !tile_begin || !tile_end)
+        return fail(MOD_ERR_ARG, "mod_plan_tile_range: null argument");
+    if (entry_begin > entry_end || entry_end > plan->n)
+        return fail(MOD_ERR_ARG, "mod_plan_tile_range: entries [%llu, %llu) outside the plan's %llu",
+                    (unsigned long long)entry_begin, (unsigned long long)entry_end, (unsigned long long)plan->n);
+    *tile_begin = plan->first_tile[entry_begin];
+    *tile_end = plan->first_tile[entry_end];
+    return MOD_OK;
+}
+
+static int plan_check_device(const mod_plan* plan, const char* who)
+{
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    if (cur != plan->device)
+        return fail(MOD_ERR_ARG, "%s: the plan lives on device %d but the calling thread is bound to device %d", who,
+                    plan->device, cur);
+    return MOD_OK;
+}
 
 int mod_plan_run(const mod_plan* plan, const void* d_src, void* d_dst, void* stream)
 {
@@ -568,6 +1083,9 @@ int mod_plan_run(const mod_plan* plan, const void* d_src, void* d_dst, void* str
     if (((uintptr_t)d_dst & 15u) != plan->dst_align)
         return fail(MOD_ERR_ALIGN, "mod_plan_run: dst & 15 is %u but the plan was built for %u",
                     (unsigned)((uintptr_t)d_dst & 15u), plan->dst_align);
+    int rc = plan_check_device(plan, "mod_plan_run");
+    if (rc != MOD_OK)
+        return rc;
     modk::BatchArgs args;
     args.src = (const uint8_t*)d_src;
     args.dst = (uint8_t*)d_dst;
@@ -581,22 +1099,75 @@ int mod_plan_run(const mod_plan* plan, const void* d_src, void* d_dst, void* str
     return MOD_OK;
 }
 
+int mod_plan_run_window(const mod_plan* plan, uint64_t tile_begin, uint64_t tile_end, const void* d_src_win,
+                        uint64_t src_win_off, uint64_t src_win_bytes, void* d_dst_win, uint64_t dst_win_off,
+                        uint64_t dst_win_bytes, void* stream)
+{
+    if (!plan)
+        return fail(MOD_ERR_ARG, "mod_plan_run_window: null plan");
+    if (tile_begin > tile_end || tile_end > plan->n_tiles)
+        return fail(MOD_ERR_ARG, "mod_plan_run_window: tiles [%llu, %llu) outside the plan's %u",
+                    (unsigned long long)tile_begin, (unsigned long long)tile_end, plan->n_tiles);
+    if (tile_begin == tile_end)
+        return MOD_OK;
+    if (!d_src_win || !d_dst_win)
+        return fail(MOD_ERR_ARG, "mod_plan_run_window: null buffer");
+    if ((((uintptr_t)d_dst_win - dst_win_off) & 15u) != plan->dst_align)
+        return fail(MOD_ERR_ALIGN, "mod_plan_run_window: (d_dst_win - dst_win_off) & 15 is %u but the plan was built for %u",
+                    (unsigned)(((uintptr_t)d_dst_win - dst_win_off) & 15u), plan->dst_align);
+    int rc = plan_check_device(plan, "mod_plan_run_window");
+    if (rc != MOD_OK)
+        return rc;
+    // every byte the tile range touches must lie inside the two windows
+    const uint32_t* ft = plan->first_tile.data();
+    uint64_t e = (uint64_t)(std::upper_bound(ft, ft + plan->n + 1, (uint32_t)tile_begin) - ft) - 1;
+    for (; e < plan->n && ft[e] < tile_end; ++e) {
+        const mod_desc& d = plan->descs[e];
+        if (ft[e + 1] == ft[e])
+            continue;  // empty entry
+        const uint32_t h0 = (uint32_t)((plan->dst_align + d.dst_off) & 15u);
+        const uint64_t ta = std::max<uint64_t>(tile_begin, ft[e]) - ft[e], tb = std::min<uint64_t>(tile_end, ft[e + 1]) - ft[e];
+        const uint64_t b0 = ta == 0 ? 0 : ta * modk::kTileBytes - h0;
+        const uint64_t b1 = std::min<uint64_t>(d.len, tb * modk::kTileBytes - h0);
+        if (d.src_off + b0 < src_win_off || d.src_off + b1 > src_win_off + src_win_bytes)
+            return fail(MOD_ERR_ARG, "mod_plan_run_window: entry %llu reads outside the source window", (unsigned long long)e);
+        if (d.dst_off + b0 < dst_win_off || d.dst_off + b1 > dst_win_off + dst_win_bytes)
+            return fail(MOD_ERR_ARG, "mod_plan_run_window: entry %llu writes outside the destination window", (unsigned long long)e);
+    }
+    modk::BatchArgs args;
+    args.src = (const uint8_t*)d_src_win - src_win_off;  // virtual bases: base + offset lands inside the window
+    args.dst = (uint8_t*)d_dst_win - dst_win_off;
+    args.tiles = plan->d_tiles + tile_begin;
+    args.n_tiles = (uint32_t)(tile_end - tile_begin);
+    args.tiles_per_entry = 0;
+    args.src_lo16 = ((uint64_t)(uintptr_t)d_src_win + 15u) & ~15ull;
+    args.src_hi16 = ((uint64_t)(uintptr_t)d_src_win + src_win_bytes) & ~15ull;
+    CUDA_TRY(modk::launch_batch(args, (cudaStream_t)stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return MOD_OK;
+}
+
 int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t src_bytes, void* dst,
                     uint64_t dst_bytes)
 {
+    MOD_ABI_BEGIN
     if (n == 0)
         return MOD_OK;
+    if (!descs)
+        return fail(MOD_ERR_ARG, "mod_cycle_batch: descs is null");
     if (!src || !dst)
         return fail(MOD_ERR_ARG, "mod_cycle_batch: null buffer");
-    int rc = ensure_ready(-1);
-    if (rc != MOD_OK)
-        return rc;
-    const bool src_dev = is_device_pointer(src), dst_dev = is_device_pointer(dst);
-    if (src_dev != dst_dev)
-        return fail(MOD_ERR_ARG, "mod_cycle_batch: src and dst must both be host or both be device pointers");
+    int src_dev = -1, dst_dev = -1;
+    const bool src_is_dev = pointer_device(src, &src_dev), dst_is_dev = pointer_device(dst, &dst_dev);
+    if (src_is_dev != dst_is_dev || (src_is_dev && src_dev != dst_dev))
+        return fail(MOD_ERR_ARG, "mod_cycle_batch: src and dst must both be host pointers or both live on one device");
 
-    mod_plan* plan = nullptr;
-    if (src_dev) {
+    if (src_is_dev) {
+        DeviceGuard guard;
+        int rc = guard.enter(src_dev);
+        if (rc != MOD_OK)
+            return rc;
+        mod_plan* plan = nullptr;
         rc = mod_plan_create(descs, n, src_bytes, dst_bytes, (uint32_t)((uintptr_t)dst & 15u), &plan);
         if (rc != MOD_OK)
             return rc;
@@ -608,227 +1179,45 @@ int mod_cycle_batch(const mod_desc* descs, uint64_t n, const void* src, uint64_t
         CUDA_TRY(e);
         return MOD_OK;
     }
+    DeviceCtx* c = nullptr;
+    int rc = acquire(-1, &c);
+    if (rc != MOD_OK)
+        return rc;
+    return batch_host(*c, descs, n, (const uint8_t*)src, src_bytes, (uint8_t*)dst, dst_bytes);
+    MOD_ABI_END("mod_cycle_batch")
+}
 
-    // Host buffers.  The HBM workspaces mirror the host buffers 1:1, the plan (descriptors -> tile
-    // records) is built once, and the entries are then streamed in GROUPS of consecutive
-    // descriptors (~MOD_GROUP_BYTES of payload each): group g uploads the source window its
-    // entries span, runs the batched kernel over its tile sub-range and downloads the destination
-    // runs it covers, on stream g % kPipeSlots -- so the upload of one group, the kernel of another
-    // and the download of a third overlap.  Only bytes covered by descriptors are written back,
-    // so untouched bytes of dst survive exactly like with the reference's per-entry fwrite/fread.
-    // The plan lives in grow-only scratch (pinned staging + HBM) and is built asynchronously on pipe
-    // stream 0; the other streams wait on an event before their first kernel, the host never does.
-    const bool trace = env_u64("MOD_TRACE", 0) != 0;
-    const double t_begin = now_ms();
-    if (n >= 0xFFFFFFFFull)
-        return fail(MOD_ERR_ARG, "mod_cycle_batch: too many descriptors (%llu)", (unsigned long long)n);
-    std::lock_guard<std::mutex> lock(g_ctx.mu);
-    auto done = [&](int code) { return code; };
-    if ((rc = grow_pinned(&g_ctx.h_descs, &g_ctx.h_descs_bytes, n * sizeof(modk::DevDesc))) != MOD_OK)
-        return rc;
-    uint64_t plan_tiles = 0, plan_payload = 0;
-    if ((rc = expand_descs(descs, n, src_bytes, dst_bytes, 0, (modk::DevDesc*)g_ctx.h_descs, &plan_tiles, &plan_payload)) != MOD_OK)
-        return rc;
-    if (plan_tiles == 0)
+int mod_cycle_batch_sharded(const mod_desc* descs, uint64_t n, const void* src, uint64_t src_bytes, void* dst,
+                            uint64_t dst_bytes, uint64_t dev_mask)
+{
+    MOD_ABI_BEGIN
+    if (n == 0)
         return MOD_OK;
-    if ((rc = grow(&g_ctx.ws_descs, &g_ctx.ws_descs_bytes, n * sizeof(modk::DevDesc))) != MOD_OK)
+    if (!descs)
+        return fail(MOD_ERR_ARG, "mod_cycle_batch_sharded: descs is null");
+    if (!src || !dst)
+        return fail(MOD_ERR_ARG, "mod_cycle_batch_sharded: null buffer");
+    int dev = -1;
+    if (pointer_device(src, &dev) || pointer_device(dst, &dev))
+        return fail(MOD_ERR_ARG, "mod_cycle_batch_sharded: src and dst must be host buffers");
+    int rc = validate_descs("mod_cycle_batch_sharded", descs, n, src_bytes, dst_bytes);
+    if (rc != MOD_OK)
         return rc;
-    if ((rc = grow(&g_ctx.ws_tiles, &g_ctx.ws_tiles_bytes, plan_tiles * sizeof(modk::TileRec))) != MOD_OK)
-        return rc;
-    if ((rc = grow(&g_ctx.ws_src, &g_ctx.ws_src_bytes, src_bytes)) != MOD_OK)
-        return rc;
-    if ((rc = grow(&g_ctx.ws_dst, &g_ctx.ws_dst_bytes, dst_bytes)) != MOD_OK)
-        return rc;
-    if (!g_ctx.plan_ready)
-        CUDA_TRY(cudaEventCreateWithFlags(&g_ctx.plan_ready, cudaEventDisableTiming));
-    CUDA_TRY(cudaMemcpyAsync(g_ctx.ws_descs, g_ctx.h_descs, n * sizeof(modk::DevDesc), cudaMemcpyHostToDevice,
-                             g_ctx.pipe_stream[0]));
-    CUDA_TRY(modk::launch_build_tiles((const modk::DevDesc*)g_ctx.ws_descs, (uint32_t)n, 0, (modk::TileRec*)g_ctx.ws_tiles,
-                                      (uint32_t)plan_tiles, g_ctx.pipe_stream[0]));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    CUDA_TRY(cudaEventRecord(g_ctx.plan_ready, g_ctx.pipe_stream[0]));
-    const modk::TileRec* d_tiles = (const modk::TileRec*)g_ctx.ws_tiles;
-    const double t_plan = now_ms();
-
-    struct Group {
-        uint64_t e0, e1;        // descriptor range
-        uint32_t t0, t1;        // tile range
-        uint64_t s_lo, s_hi;    // source window
-    };
-    const uint64_t group_bytes = std::max<uint64_t>(1 << 20, env_u64("MOD_GROUP_BYTES", 16ull << 20));
-    std::vector<Group> groups;
-    {
-        Group g{0, 0, 0, 0, UINT64_MAX, 0};
-        uint64_t acc = 0;
-        uint32_t tile = 0;
-        for (uint64_t i = 0; i < n; ++i) {
-            const mod_desc& d = descs[i];
-            if (d.len) {
-                g.s_lo = std::min(g.s_lo, d.src_off);
-                g.s_hi = std::max(g.s_hi, d.src_off + d.len);
-            }
-            acc += d.len;
-            tile += modk::tiles_for_entry((uint32_t)(d.dst_off & 15u), d.len);
-            if (acc >= group_bytes || i + 1 == n) {
-                g.e1 = i + 1;
-                g.t1 = tile;
-                if (g.t1 > g.t0)
-                    groups.push_back(g);
-                g = Group{i + 1, 0, tile, 0, UINT64_MAX, 0};
-                acc = 0;
-            }
-        }
-    }
-    // If the entries are not laid out in source order the windows overlap heavily and per-group
-    // uploads would move the image many times: fall back to a single group then.
-    uint64_t window_sum = 0;
-    for (const Group& g : groups)
-        window_sum += g.s_hi - g.s_lo;
-    if (window_sum > src_bytes + src_bytes / 4 + (1 << 20)) {
-        Group all{0, n, 0, (uint32_t)plan_tiles, 0, src_bytes};
-        groups.assign(1, all);
-    }
-
-    // Destination runs (maximal intervals downloaded with one copy) per group.  Two entries that are
-    // neighbours in the GLOBAL destination order and less than 16 bytes apart (alignment padding) are
-    // bridged into one run; the host bytes of such a gap are saved first and put back after the
-    // download, so every byte not covered by a descriptor keeps its value.  A batch whose destination
-    // is full of larger holes (more than 64 runs in a group) is handled exactly but without
-    // pipelining: the whole destination makes a round trip through HBM.
-    std::vector<uint32_t> rank(n, 0);      // position of each non-empty entry in global dst order
-    std::vector<uint8_t> bridge_after;     // by rank: the gap to the next entry may be bridged
-    {
-        std::vector<uint32_t> order;
-        order.reserve(n);
-        bool monotone = true;
-        uint64_t last = 0;
-        for (uint64_t i = 0; i < n; ++i) {
-            if (!descs[i].len)
-                continue;
-            if (descs[i].dst_off < last)
-                monotone = false;
-            last = descs[i].dst_off;
-            order.push_back((uint32_t)i);
-        }
-        if (!monotone)
-            std::sort(order.begin(), order.end(),
-                      [&](uint32_t a, uint32_t b) { return descs[a].dst_off < descs[b].dst_off; });
-        bridge_after.assign(order.size(), 0);
-        for (size_t r = 0; r < order.size(); ++r) {
-            rank[order[r]] = (uint32_t)r;
-            if (r + 1 < order.size()) {
-                const uint64_t end = descs[order[r]].dst_off + descs[order[r]].len;
-                const uint64_t nxt = descs[order[r + 1]].dst_off;
-                bridge_after[r] = (nxt >= end && nxt - end < 16) ? 1 : 0;
-            }
-        }
-    }
-    struct Gap {
-        uint64_t off;
-        uint32_t len;
-        uint8_t bytes[15];
-    };
-    std::vector<Gap> gaps;
-    std::vector<uint32_t> members;
-    auto merged_runs = [&](const Group& g, std::vector<std::pair<uint64_t, uint64_t>>& runs, bool save_gaps) {
-        runs.clear();
-        members.clear();
-        for (uint64_t i = g.e0; i < g.e1; ++i)
-            if (descs[i].len)
-                members.push_back((uint32_t)i);
-        std::sort(members.begin(), members.end(), [&](uint32_t a, uint32_t b) { return rank[a] < rank[b]; });
-        uint32_t prev_rank = 0;
-        for (uint32_t idx : members) {
-            const uint64_t b0 = descs[idx].dst_off, b1 = b0 + descs[idx].len;
-            const bool adjacent = !runs.empty() && rank[idx] == prev_rank + 1;
-            if (adjacent && b0 <= runs.back().second) {
-                runs.back().second = std::max(runs.back().second, b1);
-            } else if (adjacent && bridge_after[prev_rank] && b0 - runs.back().second < 16) {
-                if (save_gaps && b0 > runs.back().second) {
-                    Gap gap;
-                    gap.off = runs.back().second;
-                    gap.len = (uint32_t)(b0 - runs.back().second);
-                    std::memcpy(gap.bytes, (const uint8_t*)dst + gap.off, gap.len);
-                    gaps.push_back(gap);
-                }
-                runs.back().second = b1;
-            } else {
-                runs.emplace_back(b0, b1);
-            }
-            prev_rank = rank[idx];
-        }
-    };
-    std::vector<std::pair<uint64_t, uint64_t>> runs;
-    bool holes = false;
-    for (const Group& g : groups) {
-        merged_runs(g, runs, false);
-        if (runs.size() > 64) {
-            holes = true;
-            break;
-        }
-    }
-    if (holes) {
-        Group all{0, n, 0, (uint32_t)plan_tiles, 0, src_bytes};
-        groups.assign(1, all);
-    }
-
-    const uint64_t src_lo16 = ((uint64_t)(uintptr_t)g_ctx.ws_src + 15u) & ~15ull;
-    const uint64_t src_hi16 = ((uint64_t)(uintptr_t)g_ctx.ws_src + src_bytes) & ~15ull;
-    cudaError_t e = cudaSuccess;
-    for (size_t gi = 0; gi < groups.size() && e == cudaSuccess; ++gi) {
-        const Group& g = groups[gi];
-        cudaStream_t s = g_ctx.pipe_stream[gi % kPipeSlots];
-        e = cudaMemcpyAsync((uint8_t*)g_ctx.ws_src + g.s_lo, (const uint8_t*)src + g.s_lo, g.s_hi - g.s_lo,
-                            cudaMemcpyHostToDevice, s);
-        if (e == cudaSuccess && holes)
-            e = cudaMemcpyAsync(g_ctx.ws_dst, dst, dst_bytes, cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess)
-            break;
-        if (!holes)
-            merged_runs(g, runs, true);
-        modk::BatchArgs args;
-        args.src = (const uint8_t*)g_ctx.ws_src;
-        args.dst = (uint8_t*)g_ctx.ws_dst;
-        if (gi > 0 && gi < (size_t)kPipeSlots) {  // first use of this stream: the plan must be complete
-            e = cudaStreamWaitEvent(s, g_ctx.plan_ready, 0);
-            if (e != cudaSuccess)
-                break;
-        }
-        args.tiles = d_tiles + g.t0;
-        args.n_tiles = g.t1 - g.t0;
-        args.tiles_per_entry = 0;
-        args.src_lo16 = src_lo16;
-        args.src_hi16 = src_hi16;
-        e = modk::launch_batch(args, s);
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        if (e != cudaSuccess)
-            break;
-        if (holes) {
-            e = cudaMemcpyAsync(dst, g_ctx.ws_dst, dst_bytes, cudaMemcpyDeviceToHost, s);
-        } else {
-            for (const auto& r : runs) {
-                e = cudaMemcpyAsync((uint8_t*)dst + r.first, (const uint8_t*)g_ctx.ws_dst + r.first,
-                                    r.second - r.first, cudaMemcpyDeviceToHost, s);
-                if (e != cudaSuccess)
-                    break;
-            }
-        }
-    }
-    const double t_enq = now_ms();
-    for (int k = 0; k < kPipeSlots; ++k) {
-        cudaError_t es = cudaStreamSynchronize(g_ctx.pipe_stream[k]);
-        if (e == cudaSuccess)
-            e = es;
-    }
-    if (e == cudaSuccess)
-        for (const Gap& gap : gaps)  // put the padding bytes the bridged downloads ran over back
-            std::memcpy((uint8_t*)dst + gap.off, gap.bytes, gap.len);
-    if (trace)
-        fprintf(stderr, "[mod] cycle_batch: plan %.2f ms, enqueue %zu groups %.2f ms, drain %.2f ms\n", t_plan - t_begin,
-                groups.size(), t_enq - t_plan, now_ms() - t_enq);
-    if (e != cudaSuccess)
-        return done(fail(MOD_ERR_CUDA, "mod_cycle_batch: %s", cudaGetErrorString(e)));
-    return done(MOD_OK);
+    return for_each_device(dev_mask, [=](int rank, int world, DeviceCtx& c) -> int {
+        if (world == 1)
+            return batch_host(c, descs, n, (const uint8_t*)src, src_bytes, (uint8_t*)dst, dst_bytes);
+        const int64_t count = mod_shard_descs(descs, n, rank, world, nullptr, 0);
+        if (count < 0)
+            return (int)count;
+        if (count == 0)
+            return MOD_OK;
+        std::vector<mod_desc> shard((size_t)count);
+        const int64_t got = mod_shard_descs(descs, n, rank, world, shard.data(), (uint64_t)count);
+        if (got < 0)
+            return (int)got;
+        return batch_host(c, shard.data(), (uint64_t)got, (const uint8_t*)src, src_bytes, (uint8_t*)dst, dst_bytes);
+    });
+    MOD_ABI_END("mod_cycle_batch_sharded")
 }
 
 /* ---- offset-range sharding (pure host logic) ------------------------------------------------------ */

@@ -8,6 +8,9 @@ ctypes handles onto the CPU checkers:
   (``CArk.cpp:494``, ``:807-811``).
 * ``_ref/libcycle_ref.so`` -- the UNMODIFIED reference ``CEncryptionCycler.cpp`` compiled by
   ``oracle/Makefile`` (present when built in the dev container; travels to the GPU box).
+* ``_ref/libark_ref.so``   -- the reference's own ``CArk.cpp`` / ``CDtaFile.cpp`` / ``Utils.cpp`` behind
+  ``ref_ark/ark_ref_shim.cpp`` (Win32 stand-ins in ``ref_ark/``); used only by
+  ``tests/golden/make_ark_golden.py`` to write the HDR / ARK / DTB fixtures under ``tests/golden/``.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs may import this package.  Parity status: pinned (see
@@ -24,6 +27,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 _REF = os.path.join(_HERE, "_ref", "libcycle_ref.so")
+_ARK_REF = os.path.join(_HERE, "_ref", "libark_ref.so")
 
 M = 0x7FFFFFFF
 A = 16807
@@ -53,6 +57,9 @@ def build(force: bool = False) -> None:
     if os.path.exists("/root/reference/Modulate/CEncryptionCycler.cpp") and \
             (force or not os.path.exists(_REF)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    # the reference's own CArk / CDtaFile (fixture generator tests/golden/make_ark_golden.py only)
+    if os.path.exists("/root/reference/Modulate/CArk.cpp") and (force or not os.path.exists(_ARK_REF)):
+        subprocess.check_call(["make", "-C", _HERE, "ark_ref"], stdout=subprocess.DEVNULL)
 
 
 _lib = None

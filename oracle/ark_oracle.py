@@ -2,16 +2,15 @@
 
 CPU restatement (plain Python / numpy) of the parts of the reference's ``CArk`` that sit either
 side of the hot path: the ``.hdr`` on-disk format, ``LoadArkData``'s part concatenation,
-``ExtractFiles``' gather and ``BuildArk``'s offset / part-size assignment.  ``CArk.cpp`` cannot be
-compiled in this container (``<windows.h>``, ``<direct.h>``, ``fopen_s``, MSVC-only template
-syntax pulled in through ``CDtaFile.h``), so this restatement follows the
-cited line ranges instead.  Only ``tests/`` imports it.
+``ExtractFiles``' gather and ``BuildArk``'s offset / part-size assignment.  Only ``tests/`` imports it.
 
-Parity status: the cipher under the header is PINNED (it is ``oracle.cycle``, checked against
-the unmodified reference).  The header LAYOUT restated here is UNPINNED by execution -- the
-reference has no tests or sample archives and its CArk cannot be built here -- and is anchored on
-the reference's own reader and writer agreeing with each other (``Load`` CArk.cpp:341-416 parses
-what ``lSaveHeader`` CArk.cpp:911-1133 writes), which the tests check as a round trip.
+Parity status: PINNED by executing the reference.  ``make -C oracle ark_ref`` compiles the
+reference's own ``CArk.cpp`` (Win32 calls resolved by the stand-ins in ``oracle/ref_ark/``) and
+``tests/golden/make_ark_golden.py`` commits the headers it wrote, the tables it parsed and the part
+sizes it assigned (``tests/golden/ark/``); ``tests/test_ref_fixtures.py`` checks this restatement's
+reader, PS3 and PS4 writers and ``build_ark`` against them (header bytes 12..27, uninitialised stack
+in the reference, masked).  The cipher under the header is ``oracle.cycle``, itself checked against
+the unmodified reference cipher.
 
 Citations are relative to /root/reference/Modulate/.
 """
@@ -185,11 +184,42 @@ def bucket_order_ps3(entries: Sequence[Entry]) -> List[int]:
     return sorted(range(n), key=lambda i: (file_hash(entries[i].name, n), i))
 
 
+def path_order_ps4(entries: Sequence[Entry]) -> List[int]:
+    """PS4 branch of the sort, CArk.cpp:969-1045: at every depth a leaf (file) sorts before a
+    sub-directory, names compare with _stricmp, full ties by flags1 then flags2.  The reference's
+    comparator returns true for equal elements (not a strict weak ordering), so entries that tie
+    completely -- the same name twice -- have no defined order; for distinct names this is a total
+    order and the reference-written PS4 fixtures confirm it."""
+    import functools
+
+    def stricmp(a: str, b: str) -> int:
+        la, lb = a.lower(), b.lower()
+        return (la > lb) - (la < lb)
+
+    paths = [e.name.split("/") for e in entries]
+
+    def cmp(i: int, j: int) -> int:
+        a, b = paths[i], paths[j]
+        d = 0
+        while True:
+            a_leaf, b_leaf = d + 1 == len(a), d + 1 == len(b)
+            if a_leaf != b_leaf:
+                return -1 if a_leaf else 1
+            c = stricmp(a[d], b[d])
+            if c:
+                return c
+            if a_leaf:
+                ka = (entries[i].flags1, entries[i].flags2, i)
+                kb = (entries[j].flags1, entries[j].flags2, j)
+                return (ka > kb) - (ka < kb)
+            d += 1
+
+    return sorted(range(len(entries)), key=functools.cmp_to_key(cmp))
+
+
 def serialise_header(hdr: Header, order: Optional[Sequence[int]] = None, checksum: bytes = b"\0" * 16) -> bytes:
     """Plaintext header bytes in the order lSaveHeader emits them.  `order` is the entry order
-    (default: the PS3 bucket order, which is a well-defined total order; the PS4 branch's
-    comparator, CArk.cpp:969-1045, is not a strict weak ordering, so its result is whatever the
-    reference's std::sort happens to do and cannot be restated).  The 16 checksum bytes are
+    (default: the platform's -- PS3 by name-hash bucket, PS4 by path).  The 16 checksum bytes are
     uninitialised stack in the reference (CArk.cpp:911-921) and zero here."""
     n = len(hdr.entries)
     out = bytearray()
@@ -204,7 +234,7 @@ def serialise_header(hdr: Header, order: Optional[Sequence[int]] = None, checksu
     out += struct.pack("<i", len(hdr.parts)) + b"\0" * (4 * len(hdr.parts))  # string counts, :955-961
     out += struct.pack("<i", n)
     if order is None:
-        order = bucket_order_ps3(hdr.entries)
+        order = path_order_ps4(hdr.entries) if hdr.ps4 else bucket_order_ps3(hdr.entries)
     hashes = [file_hash(hdr.entries[i].name, n) for i in order]
     # bucket chain threading, CArk.cpp:1064-1110 (restated literally, including the way a bucket
     # that re-appears later is looked up through the FIRST pair pushed for it)

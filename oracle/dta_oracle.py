@@ -3,9 +3,11 @@
 Plain-Python restatement of the reference's binary DTA ("DTB") reader and writer:
 ``CDtaFile::Load`` / ``AddTreeNode`` (CDtaFile.cpp:57-100, :393-509) and ``CDtaFile::Save`` /
 ``SaveToStream`` (CDtaFile.cpp:362-391, :1302-1326; CDtaFile.h:262-284).  ``CDtaFile.cpp`` cannot be
-compiled in this container (MSVC-only explicit specialisations without ``template<>``,
-CDtaFile.h:262-284), so parity is UNPINNED by execution and anchored on the reference's reader and
-writer agreeing with each other (round trip).  Only ``tests/`` imports this module.
+compiled unmodified here (MSVC-only explicit specialisations without ``template<>``,
+CDtaFile.h:262-284), so ``make -C oracle ark_ref`` stages it, fixes those four declarations
+(``oracle/ref_ark/patch.sed``) and builds it; parity is PINNED by the DTB fixtures the reference's
+own Load + Save produced (``tests/golden/dtb/``, ``tests/test_ref_fixtures.py``).  Only ``tests/``
+imports this module.
 
 A tree is ``("tree", type, node_id, [children])``; leaves are ``("int", type, value)``,
 ``("float", 1, value)``, ``("str", type, bytes)``.
@@ -108,6 +110,16 @@ def serialise(trees: List[Tuple]) -> bytes:
     for i, t in enumerate(trees):
         if i:
             out += struct.pack("<ii", t[1], 1)
+        _write_tree(t, out)
+    return bytes(out)
+
+
+def save_like_reference(trees: List[Tuple]) -> bytes:
+    """CDtaFile::Save exactly as written, CDtaFile.cpp:364-374: the root's children are streamed back
+    to back, WITHOUT the (type, 1) words Load consumes between top-level trees -- so only single-tree
+    files round-trip through the reference (pinned by tests/golden/dtb/two_trees)."""
+    out = bytearray(b"\x01" + struct.pack("<i", 1))
+    for t in trees:
         _write_tree(t, out)
     return bytes(out)
 

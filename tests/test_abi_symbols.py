@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_desc_layout():
     from modulate_b200 import _abi, DESC_DTYPE
-    assert _abi.load().mod_abi_version() == 1
+    assert _abi.load().mod_abi_version() == 2
     assert ctypes.sizeof(_abi.ModDesc) == 24 == DESC_DTYPE.itemsize
 
 

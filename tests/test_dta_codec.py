@@ -1,5 +1,6 @@
 """CPU: the host-side DTB codec (csrc/CDtaFile.cpp) through the CLI built against the mock ABI,
-checked against the oracle restatement of the reference's reader/writer (oracle/dta_oracle.py)."""
+checked against the oracle restatement of the reference's reader/writer (oracle/dta_oracle.py), which
+tests/test_ref_fixtures.py in turn checks against DTB files the reference itself loaded and saved."""
 import struct
 
 import numpy as np
@@ -57,7 +58,11 @@ def test_cpp_codec_roundtrips_random_trees(cli, tmp_path, seed):
     assert do.parse(blob) == trees
     (tmp_path / "in.dtb").write_bytes(blob)
     run(cli, tmp_path, "-dtacopy", "in.dtb", "out.dtb")
-    assert (tmp_path / "out.dtb").read_bytes() == blob
+    # what the reference's Save writes: identical for one tree, separator-less for several (pinned by
+    # tests/golden/dtb/two_trees, tests/test_ref_fixtures.py)
+    assert (tmp_path / "out.dtb").read_bytes() == do.save_like_reference(trees)
+    if len(trees) == 1:
+        assert do.save_like_reference(trees) == blob
 
 
 def test_cpp_dtaset_patches_like_the_oracle(cli, tmp_path):
