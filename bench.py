@@ -1,25 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- ARK/DTB decrypt throughput on B200 (BASELINE.json metric), one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3|cfg2|cfg4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload = "cfg2", BASELINE.json configs[1]): a synthetic 1 GiB ARK image holding
-10 000 byte-packed entries (sizes log-uniform 1 KiB..1 MiB, BuildArk order, reference
-CArk.cpp:807-811) plus its encrypted HDR.  One STEP = what `-unpack` does to it on the hot path:
-    1. CEncryptionCycler::Cycle over the HDR past its 4-byte magic (CArk::Load, CArk.cpp:338-339);
-    2. one launch of the variable-length batched kernel that gathers every entry out of the image
-       (CArk::ExtractFiles, CArk.cpp:494) while decrypting it with its per-entry key, each entry
-       landing in its own 16-byte-aligned slot of the extract buffer.
-`value` times that with the image resident in HBM; `e2e` times the same work through the public
-C ABI on HOST buffers (pinned), H2D and D2H copies included.  At N > 1 the set is N such parts
-(N GiB), cut into N equal-payload shards by mod_shard_descs (entries that straddle a boundary are
-split and the tail gets the jumped key); one process per GPU, no collective on the data path
-(weak scaling: 1 GiB of payload per GPU).
+Headline workload (config.workload = "cfg3", BASELINE.json configs[2], the north_star target): a
+16 GiB multi-part ARK set = 32 parts x 512 MiB (kuMaxArkSize, reference CArk.cpp:19), one
+(offset, len, key) per part, ciphered in place.  One STEP = one pass of the hot path over the set:
+    1. CEncryptionCycler::Cycle over the 384 KiB HDR past its 4-byte magic (CArk::Load, CArk.cpp:338-339;
+       rank 0 only -- there is one header);
+    2. one launch of the variable-length batched kernel over this rank's share of the set.
+STRONG scaling: the set is fixed; at N GPUs it is cut into N equal-payload offset ranges by
+mod_shard_descs (cuts fall inside parts: the tail piece starts from the jumped key), one process per
+GPU, no collective on the data path.  `value` times the steps with the set resident in HBM; `e2e`
+times the same work through the public C ABI on pinned HOST buffers, H2D and D2H copies included.
 
-The CPU numbers come from the UNMODIFIED reference cipher (oracle/_ref, built from
-/root/reference/Modulate/CEncryptionCycler.cpp) fanned out over the host cores, one reference
-Cycle() per entry; they are a baseline, not the target -- the target is roofline.frac.
+Parity is checked IN THIS RUN, at every N, on every rank, before the timed region: >= 64 MiB of
+windows of the rank's own shard (both sides of every interior cut and part boundary, plus random
+windows) are byte-compared with the CPU oracle -- the unmodified reference cipher (oracle/_ref) for
+windows that start a part, its closed-form restatement (pinned against it) for windows deep inside
+one.  `parity_bytes_checked` is the sum over ranks; any mismatch ends the run with rc != 0.
+
+At N == 1 the line also carries `extra.cfg2` (1 GiB / 10 000 entries, misaligned gather; BASELINE
+configs[1]) and `extra.cfg4` (1 000 000 entries of 1..64 KiB, one launch; configs[3]), each with its
+own roofline and parity count, `roofline.sustained` (>= 3 s of back-to-back launches with NVML clock /
+power samples) next to the burst figure, and `cpu_baseline` (the unmodified reference cipher on the
+host cores, bounded sample).  The CPU numbers are a baseline, not the target -- the target is
+roofline.frac.
 """
 from __future__ import annotations
 
@@ -40,56 +47,59 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import synth  # noqa: E402  (synthetic inputs shared with the tests)
 
 GIB = 1 << 30
+MIB = 1 << 20
 HDR_BYTES = 384 * 1024  # a real main_ps4.hdr is 0.3-0.5 MB
+PART = 512 * MIB        # kuMaxArkSize, reference CArk.cpp:19
+N_PARTS = 32
+CPU_SAMPLE_PER_PART = 32 * MIB
+PARITY_TARGET = 64 * MIB
+METRIC = "ark_dtb_decrypt_throughput"
 
 
 # ---- workload construction --------------------------------------------------------------------
 
-def cfg2_entries(part: int = 0):
-    """Entry table of one 1 GiB part: (src_off within the set, size, key)."""
-    sizes = synth.entry_sizes_loguniform(10_000, GIB, lo=1 << 10, hi=1 << 20, seed=7 + part)
-    src_off = synth.packed_offsets(sizes) + part * GIB
-    keys = synth.entry_keys(len(sizes), seed=synth.SEED + part)
-    return src_off, sizes, keys
+def cfg2_entries():
+    """Entry table of the 1 GiB archive: (src_off, size, key)."""
+    sizes = synth.entry_sizes_loguniform(10_000, GIB, lo=1 << 10, hi=1 << 20, seed=7)
+    return synth.packed_offsets(sizes), sizes, synth.entry_keys(len(sizes), seed=synth.SEED)
 
 
-def cfg4_entries(part: int = 0, n: int = 250_000):
-    """Many small DTB files: n entries of 1..64 KiB with per-file keys (configs[3] shape; 250k
-    entries ~ 8 GiB per GPU instead of 1M ~ 32.5 GiB so that setup stays within the bench budget)."""
-    rng = np.random.default_rng(40 + part)
+def cfg4_entries(n: int = 1_000_000):
+    """BASELINE configs[3]: n byte-packed entries of 1..64 KiB with per-entry keys (~32.5 GiB at 1M)."""
+    rng = np.random.default_rng(40)
     sizes = rng.integers(1 << 10, (64 << 10) + 1, size=n).astype(np.int64)
-    base = part * (n * (64 << 10))
-    src_off = synth.packed_offsets(sizes) + base
-    keys = synth.entry_keys(n, seed=synth.SEED + 99 + part)
-    return src_off, sizes, keys
+    return synth.packed_offsets(sizes), sizes, synth.entry_keys(n, seed=synth.SEED + 99)
 
 
 def aligned_slots(sizes: np.ndarray) -> np.ndarray:
     """Each extracted file gets its own 16-byte-aligned slot (separately allocated outputs)."""
-    padded = (sizes + 15) & ~np.int64(15)
-    return synth.packed_offsets(padded)
+    return synth.packed_offsets((sizes + 15) & ~np.int64(15))
 
 
-def cfg3_descs(mb):
-    """16 GiB multi-part set: 32 parts x 512 MiB (kuMaxArkSize, reference CArk.cpp:19), one
-    (offset, len, key) per part, ciphered in place (BASELINE configs[2])."""
-    part = 512 << 20
-    off = np.arange(32, dtype=np.int64) * part
-    return mb.make_descs(off, off, np.full(32, part, np.int64), synth.entry_keys(32, seed=synth.SEED + 3))
-
-
-def build_global_descs(mb, workload: str, world: int):
+def global_descs(mb, workload: str, cfg4_n: int = 1_000_000) -> np.ndarray:
     if workload == "cfg3":
-        return cfg3_descs(mb)
-    offs, sizes, keys = [], [], []
-    for part in range(world):
-        o, s, k = cfg2_entries(part) if workload == "cfg2" else cfg4_entries(part)
-        offs.append(o), sizes.append(s), keys.append(k)
-    src_off = np.concatenate(offs)
-    size = np.concatenate(sizes)
-    key = np.concatenate(keys)
-    dst_off = aligned_slots(size)
-    return mb.make_descs(src_off, dst_off, size, key)
+        off = np.arange(N_PARTS, dtype=np.int64) * PART
+        return mb.make_descs(off, off, np.full(N_PARTS, PART, np.int64), synth.entry_keys(N_PARTS, seed=synth.SEED + 3))
+    if workload == "cfg2":
+        off, size, key = cfg2_entries()
+        return mb.make_descs(off, aligned_slots(size), size, key)
+    off, size, key = cfg4_entries(cfg4_n)
+    return mb.make_descs(off, off, size, key)  # in place, like config 3
+
+
+def config_block(workload: str, descs: np.ndarray, world: int) -> dict:
+    """Identical in both arms (ours / reference) so the driver sees the same config."""
+    layout = {
+        "cfg3": "16 GiB = 32 parts x 512 MiB (kuMaxArkSize), one (offset, len, key) per part, ciphered in place; "
+                "HDR Cycle + one batched launch per step",
+        "cfg2": "1 GiB image, 10 000 byte-packed entries (log-uniform 1 KiB..1 MiB), per-entry keys, gathered into "
+                "16-byte-aligned extract slots; HDR Cycle + one batched launch per step",
+        "cfg4": "byte-packed entries of 1..64 KiB, per-entry keys, ciphered in place; HDR Cycle + one batched launch per step",
+    }[workload]
+    return {"workload": workload, "entries": int(len(descs)), "payload_bytes": int(descs["len"].sum()),
+            "hdr_bytes": HDR_BYTES, "layout": layout,
+            "l2": "every step reads and writes far more than the 126 MB L2 (>= 2 GiB per GPU); no flush needed",
+            "sharding": "mod_shard_descs equal-payload offset ranges over n_gpus, no collective (strong scaling)"}
 
 
 def rebase(descs: np.ndarray):
@@ -106,16 +116,49 @@ def rebase(descs: np.ndarray):
     return out, s0, d0, src_bytes, dst_bytes
 
 
+# ---- synthetic payload on the device ---------------------------------------------------------------
+
+def _i64(c: int) -> int:
+    c &= (1 << 64) - 1
+    return c - (1 << 64) if c >> 63 else c
+
+
+def device_payload(torch, out, offset: int, seed: int = synth.SEED, slice_bytes: int = 256 * MIB) -> None:
+    """Fill the uint8 tensor `out` with synth.payload(offset, len(out)) -- the same counter-based
+    splitmix64 stream, generated where the tensor lives (two's-complement int64 arithmetic wraps like
+    uint64; logical shifts are arithmetic shifts with the sign bits masked off)."""
+    n = out.numel()
+
+    def lsr(z, k):
+        return (z >> k) & ((1 << (64 - k)) - 1)
+
+    pos = 0
+    while pos < n:
+        m = min(slice_bytes, n - pos)
+        w0 = (offset + pos) // 8
+        w1 = (offset + pos + m + 7) // 8
+        x = torch.arange(w0, w1, dtype=torch.int64, device=out.device)
+        x = (x ^ _i64(seed)) + _i64(0x9E3779B97F4A7C15)
+        z = (x ^ lsr(x, 30)) * _i64(0xBF58476D1CE4E5B9)
+        z = (z ^ lsr(z, 27)) * _i64(0x94D049BB133111EB)
+        z = z ^ lsr(z, 31)
+        b = z.view(torch.uint8)
+        lo = (offset + pos) - w0 * 8
+        out[pos:pos + m].copy_(b[lo:lo + m])
+        pos += m
+        del x, z, b
+
+
 # ---- clocks -------------------------------------------------------------------------------------
 
 class ClockSampler:
-    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    """Samples SM clock, power and throttle reasons of one GPU through NVML while a region runs."""
     REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
                0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
-    def __init__(self, index: int, period_s: float = 0.004):
-        self.samples, self.reasons, self.power = [], set(), []
+    def __init__(self, index: int, period_s: float = 0.002):
+        self.samples, self.power, self.reason_counts = [], [], {}
         self.max_mhz = None
         self.period = period_s
         self._stop = threading.Event()
@@ -129,24 +172,28 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
-    def _run(self):
+    def _sample(self):
         nv = self.nv
+        try:
+            self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
+                nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            for bit, name in self.REASONS.items():
+                if mask & bit and name != "gpu_idle":
+                    self.reason_counts[name] = self.reason_counts.get(name, 0) + 1
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+
+    def _run(self):
         while not self._stop.is_set():
-            try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
-                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(
-                    nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                for bit, name in self.REASONS.items():
-                    if mask & bit and name != "gpu_idle":
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
-            except Exception:
-                pass
+            self._sample()
             time.sleep(self.period)
 
     def start(self):
         if self.nv is not None:
+            self._sample()
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
 
@@ -154,81 +201,85 @@ class ClockSampler:
         self._stop.set()
         if self._thread is not None:
             self._thread.join(timeout=2)
+        if self.nv is not None:
+            self._sample()
         med = float(np.median(self.samples)) if self.samples else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.samples), "power_w_max": max(self.power) if self.power else None}
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reason_counts),
+                "reason_samples": dict(self.reason_counts), "samples": len(self.samples),
+                "sm_mhz_min": min(self.samples) if self.samples else None,
+                "power_w_max": max(self.power) if self.power else None,
+                "power_w_mean": float(np.mean(self.power)) if self.power else None}
 
 
 # ---- CPU arm: the unmodified reference cipher on the host cores ------------------------------------
 
-def zeros_payload(offset: int, n: int) -> np.ndarray:
-    return np.zeros(n, dtype=np.uint8)
-
-
-def cpu_reference_setup(descs: np.ndarray, target_seconds: float = 1.5, payload_fn=None):
-    """Pick a bounded sample (whole entries from the front of the table) that the reference cipher,
-    fanned out over all host threads, finishes in about `target_seconds`."""
+def cpu_sample(descs: np.ndarray, workload: str):
+    """Bounded sample of the workload for the CPU arm: one reference Cycle() per entry / part prefix,
+    fanned out over all host threads (the reference has no jump-ahead, so a part can only be sampled
+    from its start).  cfg3: the first 32 MiB of each of the 32 parts (1 GiB).  cfg2: every entry (1 GiB).
+    cfg4: the first 32 768 entries (~1 GiB)."""
     import oracle
-    kind = "reference" if oracle.have_ref() else "port"
-    cores = os.cpu_count() or 1
-    probe = synth.payload(0, 8 << 20)
+    d = descs
+    if workload == "cfg3":
+        d = descs.copy()
+        d["len"] = np.minimum(d["len"], CPU_SAMPLE_PER_PART)
+        what = f"the first {CPU_SAMPLE_PER_PART >> 20} MiB of each of the {len(d)} parts"
+    elif workload == "cfg4":
+        d = descs[:32768]
+        what = f"the first {len(d)} entries"
+    else:
+        what = f"all {len(d)} entries"
+    parts = np.zeros(len(d), dtype=oracle.PART_DTYPE)
+    parts["off"] = synth.packed_offsets(d["len"].astype(np.int64))  # sample bytes packed back to back
+    parts["len"] = d["len"]
+    parts["key"] = d["key"]
+    nbytes = int(d["len"].sum())
+    return {"descs": d, "parts": parts, "bytes": nbytes,
+            "sample": f"{what} of the {workload} set ({nbytes} payload bytes) per step, one reference Cycle() each"}
+
+
+def cpu_fill_plain(sample, buf: np.ndarray) -> None:
+    """The sample's plaintext: synth.payload at each entry's SOURCE offset in the full set."""
+    for p, d in zip(sample["parts"], sample["descs"]):
+        o, n = int(p["off"]), int(p["len"])
+        buf[o:o + n] = synth.payload(int(d["src_off"]), n)
+
+
+def cpu_step(sample, work: np.ndarray, cores: int, kind: str) -> float:
+    import oracle
     t0 = time.perf_counter()
     if kind == "reference":
-        oracle.ref().ref_cycle(probe.ctypes.data, probe.size, 12345)
-    else:
-        oracle.lib().oracle_cycle(probe.ctypes.data, probe.size, 12345)
-    rate1 = probe.size / (time.perf_counter() - t0)
-    budget = rate1 * cores * target_seconds
-    csum = np.cumsum(descs["len"].astype(np.int64))
-    n = int(np.searchsorted(csum, budget, side="right"))
-    n = max(min(n, len(descs)), min(len(descs), 4 * cores if int(descs["len"].max()) < (64 << 20) else 1))
-    sample = descs[:n]
-    lo = int(sample["src_off"].min())
-    hi = int((sample["src_off"] + sample["len"]).max())
-    plain = (payload_fn or synth.payload)(lo, hi - lo)
-    parts = np.zeros(n, dtype=oracle.PART_DTYPE)
-    parts["off"] = sample["src_off"] - lo
-    parts["len"] = sample["len"]
-    parts["key"] = sample["key"]
-    return {"kind": kind, "cores": cores, "parts": parts, "plain": plain, "lo": lo,
-            "bytes": int(sample["len"].sum()), "n": n, "rate1": rate1}
-
-
-def cpu_reference_step(setup, work: np.ndarray) -> float:
-    """One pass of the sample: one reference Cycle() per entry over all host threads. Returns seconds."""
-    import oracle
-    np.copyto(work, setup["plain"])
-    t0 = time.perf_counter()
-    if setup["kind"] == "reference":
-        oracle.ref_cycle_parts(work, setup["parts"], setup["cores"])
+        oracle.ref_cycle_parts(work, sample["parts"], cores)
     else:  # oracle port, single-threaded C restatement
-        for p in setup["parts"]:
-            o, l = int(p["off"]), int(p["len"])
-            oracle.lib().oracle_cycle(work.ctypes.data + o, l, int(p["key"]))
+        for p in sample["parts"]:
+            oracle.lib().oracle_cycle(work.ctypes.data + int(p["off"]), int(p["len"]), int(p["key"]))
     return time.perf_counter() - t0
 
 
 def run_reference_arm(args) -> None:
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     import modulate_b200 as mb  # host-only use: make_descs (no GPU work on this arm)
-    descs = build_global_descs(mb, args.workload, 1)
-    setup = cpu_reference_setup(descs, target_seconds=1.5, payload_fn=zeros_payload if args.workload == "cfg3" else None)
-    work = np.empty_like(setup["plain"])
+    import oracle
+    kind = "reference" if oracle.have_ref() else "port"
+    descs = global_descs(mb, args.workload)
+    sample = cpu_sample(descs, args.workload)
+    cores = min(os.cpu_count() or 1, len(sample["parts"]))  # one reference Cycle() per part: at most that many threads
+    work = np.empty(sample["bytes"], dtype=np.uint8)
+    cpu_fill_plain(sample, work)
     for _ in range(args.warmup):
-        cpu_reference_step(setup, work)
+        cpu_step(sample, work, cores, kind)
     t = 0.0
     for _ in range(args.steps):
-        t += cpu_reference_step(setup, work)
-    gbs = setup["bytes"] * args.steps / t / 1e9
-    sample = f"first {setup['n']} entries ({setup['bytes']} payload bytes) of the {args.workload} archive per step"
+        t += cpu_step(sample, work, cores, kind)  # the cipher is an involution: no refill needed
+    gbs = sample["bytes"] * args.steps / t / 1e9
     line = {
-        "impl": "reference", "metric": "ark_dtb_decrypt_throughput", "value": gbs, "unit": "GB/s",
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "entries": int(len(descs)), "sample": sample},
-        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": setup["cores"], "kind": setup["kind"], "sample": sample},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": config_block(args.workload, descs, args.gpus),
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": cores if kind == "reference" else 1, "kind": kind,
+                         "sample": sample["sample"]},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -241,262 +292,411 @@ def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs: torch copy_ of 2 GiB, best of 10)"
     return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
-def run_gpu_arm(args) -> None:
-    import torch
-    import modulate_b200 as mb
+class Ctx:
+    """Per-process state shared by the measurement helpers."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    # NUMA placement: run this rank (and first-touch its pinned buffers) on the CPUs closest to its GPU
-    all_cpus = os.sched_getaffinity(0)
-    numa_pinned = False
-    try:
-        import pynvml
-        pynvml.nvmlInit()
-        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
-        numa_pinned = os.sched_getaffinity(0) != all_cpus
-    except Exception:
-        pass
-    mb.init(local)
-    dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
-    sh = stream.cuda_stream
-
-    # -- this rank's shard of the set
-    gdescs = build_global_descs(mb, args.workload, world)
-    shard = mb.shard_descs(gdescs, rank, world) if world > 1 else gdescs
-    descs, s0, d0, src_bytes, dst_bytes = rebase(shard)
-    payload = int(descs["len"].sum())
-
-    # -- inputs resident in HBM: the shard's slice of the set image, and the encrypted HDR
-    in_place = args.workload == "cfg3"  # the multi-part set is ciphered where it lies; all-zero payload
-    payload_fn = zeros_payload if in_place else synth.payload
-    step_bytes = 64 << 20
-    if in_place:
-        d_src = torch.zeros(src_bytes, dtype=torch.uint8, device=dev)
-        d_dst = d_src
-    else:
-        d_src = torch.empty(src_bytes, dtype=torch.uint8, device=dev)
-        for o in range(0, src_bytes, step_bytes):
-            n = min(step_bytes, src_bytes - o)
-            d_src[o:o + n].copy_(torch.from_numpy(synth.payload(s0 + o, n)))
-        d_dst = torch.empty(dst_bytes, dtype=torch.uint8, device=dev)
-    hdr_np = synth.payload(1 << 40, HDR_BYTES)
-    d_hdr = torch.from_numpy(hdr_np).to(dev)
-    plan = mb.Plan(descs, src_bytes, dst_bytes)
-    hdr_key = synth.PS4_KEY
-
-    def step():
-        mb.cycle_device(d_hdr.data_ptr() + 4, d_hdr.data_ptr() + 4, HDR_BYTES - 4, hdr_key, sh)
-        plan.run(d_src.data_ptr(), d_dst.data_ptr(), sh)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-
-    # -- timed region: K steps between two events; the batched kernel is also bracketed per step
-    clocks = ClockSampler(local)
-    launches0 = mb.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    clocks.start()
-    ev0.record(stream)
-    for i in range(args.steps):
-        mb.cycle_device(d_hdr.data_ptr() + 4, d_hdr.data_ptr() + 4, HDR_BYTES - 4, hdr_key, sh)
-        kev[i][0].record(stream)
-        plan.run(d_src.data_ptr(), d_dst.data_ptr(), sh)
-        kev[i][1].record(stream)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    clock_info = clocks.stop()
-    launches = mb.launch_count() - launches0
-    ms_total = ev0.elapsed_time(ev1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total_max = float(t.item())
-    total_payload = int(gdescs["len"].sum())
-    hdr_payload = (HDR_BYTES - 4) * world
-    value = (total_payload + hdr_payload) * args.steps / (ms_total_max * 1e-3) / 1e9
-
-    # -- end to end through the public C ABI with HOST (pinned) buffers: H2D + kernels + D2H per step
-    e2e_steps = max(2, min(args.steps, 5))
-    if args.kernel_only and in_place:
-        if rank == 0:
-            print(json.dumps({"kernel_ms": round(kernel_ms, 4), "payload_gbs": round(payload / (kernel_ms * 1e-3) / 1e9, 1),
-                              "value": round(value, 1), "kernel_only": True}), flush=True)
-        return
-    if args.kernel_only:
-        # tuning aid: also time (a) the co-aligned layout (extract slots at the packed source offsets)
-        # and (b) one contiguous in-place Cycle over the whole image (config 2 (i))
-        def timed(fn, n=max(5, args.steps // 2)):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(n):
-                fn()
-            b.record(stream)
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / n
-        co = descs.copy()
-        co["dst_off"] = co["src_off"]
-        d_dst2 = torch.empty(src_bytes, dtype=torch.uint8, device=dev)
-        plan2 = mb.Plan(co, src_bytes, src_bytes)
-        ms_co = timed(lambda: plan2.run(d_src.data_ptr(), d_dst2.data_ptr(), sh))
-        ms_ct = timed(lambda: mb.cycle_device(d_src.data_ptr(), d_src.data_ptr(), src_bytes, hdr_key, sh))
-        if rank == 0:
-            print(json.dumps({"kernel_ms": round(kernel_ms, 4), "extract_gbs": round(payload / (kernel_ms * 1e-3) / 1e9, 1),
-                              "coaligned_gbs": round(payload / (ms_co * 1e-3) / 1e9, 1),
-                              "contiguous_gbs": round(src_bytes / (ms_ct * 1e-3) / 1e9, 1), "value": round(value, 1),
-                              "kernel_only": True}), flush=True)
-        return
-    if in_place:
-        e2e_steps = 2
-        h_src = torch.zeros(src_bytes, dtype=torch.uint8).pin_memory()
-        h_dst = h_src
-    else:
-        h_src = torch.empty(src_bytes, dtype=torch.uint8).pin_memory()
-        h_dst = torch.empty(dst_bytes, dtype=torch.uint8).pin_memory()
-        for o in range(0, src_bytes, step_bytes):
-            n = min(step_bytes, src_bytes - o)
-            h_src[o:o + n].copy_(torch.from_numpy(synth.payload(s0 + o, n)))
-    h_hdr = torch.from_numpy(hdr_np.copy()).pin_memory()
-
-    def e2e_step():
-        mb.cycle(h_hdr.data_ptr() + 4, HDR_BYTES - 4, hdr_key)
-        mb.cycle_batch(descs, h_src.data_ptr(), h_dst.data_ptr(), src_bytes, dst_bytes)
-
-    e2e_step()
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = (total_payload + hdr_payload) * e2e_steps / float(t.item()) / 1e9
-    h2d = src_bytes + (HDR_BYTES - 4) + len(descs) * 32
-    d2h = payload + (HDR_BYTES - 4)
-
-    if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # -- roofline of the dominant kernel: algorithmic bytes = 2 per payload byte (1 read + 1 write)
-    peak, peak_src = load_peaks()
-    achieved = 2.0 * payload / (kernel_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "modk::cycle_batch_kernel", "kernel_ms": kernel_ms,
-                "algorithmic_bytes_per_launch": 2 * payload, "peak_source": peak_src,
-                "payload_gbs": payload / (kernel_ms * 1e-3) / 1e9}
-    # the co-limiting integer roofline: one IMAD.WIDE per payload byte at the measured issue rate
-    try:
-        with open(os.path.join(ROOT, "profiles", "imad.json")) as f:
-            lanes = float(json.load(f)["imad_wide_thread_instr_per_clk_per_sm"])
-        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-        mhz = clock_info.get("sm_mhz") or clock_info.get("sm_max_mhz") or 1965.0
-        imad_peak = sm_count * lanes * mhz * 1e6 / 1e9  # payload GB/s if IMAD.WIDE were the only limit
-        roofline["imad"] = {"peak_payload_gbs": imad_peak, "frac": roofline["payload_gbs"] / imad_peak,
-                            "imad_wide_per_clk_per_sm": lanes, "note": "HBM is the binding roofline"}
-    except Exception:
-        pass
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
+    def __init__(self):
+        import torch
+        import modulate_b200 as mb
+        self.torch, self.mb = torch, mb
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.dist = None
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        # NUMA placement: run this rank (and first-touch its pinned buffers) on the CPUs closest to its GPU
+        self.all_cpus = os.sched_getaffinity(0)
+        self.numa_pinned = False
         try:
-            with open(traffic_file) as f:
-                roofline["traffic"] = json.load(f).get(args.workload)
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(self.local))
+            self.numa_pinned = os.sched_getaffinity(0) != self.all_cpus
         except Exception:
             pass
+        mb.init(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.stream = torch.cuda.current_stream()
+        self.sh = self.stream.cuda_stream
+        self.peak, self.peak_src = load_peaks()
 
-    # -- CPU baseline on this box (N == 1 only): the unmodified reference on a bounded sample, and a
-    #    byte-for-byte check of the GPU output of those entries against it
-    cpu = None
-    if world == 1:
-        os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core
-        setup = cpu_reference_setup(gdescs, target_seconds=2.0, payload_fn=payload_fn)
-        work = np.empty_like(setup["plain"])
-        cpu_reference_step(setup, work)
-        secs = min(cpu_reference_step(setup, work) for _ in range(3))
-        if in_place:  # an odd number of passes so far would leave the image ciphered; start from zeros
-            d_src.zero_()
-        step()
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, value: float, op: str) -> float:
+        if self.dist is None:
+            return float(value)
+        t = self.torch.tensor([value], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def finish(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def parity_windows(descs: np.ndarray, target: int, rng) -> list:
+    """(entry index, position in entry, length) windows of a shard: both ends of every piece (= both
+    sides of every interior cut and part boundary, the neighbour rank checks the other side), then
+    random windows until `target` bytes."""
+    wins, total = [], 0
+    edge = 256 << 10
+    for i, d in enumerate(descs):
+        n = int(d["len"])
+        if n == 0:
+            continue
+        if n <= 2 * edge:
+            wins.append((i, 0, n))
+            total += n
+        else:
+            wins.append((i, 0, edge))
+            wins.append((i, n - edge, edge))
+            total += 2 * edge
+        if total >= target and len(descs) > 4096:  # many-entry sets: a sample of entries is enough
+            break
+    big = [i for i, d in enumerate(descs) if int(d["len"]) > 4 * MIB]
+    while total < target and big:
+        i = big[int(rng.integers(0, len(big)))]
+        n = int(descs[i]["len"])
+        w = min(4 * MIB, n)
+        wins.append((i, int(rng.integers(0, n - w + 1)), w))
+        total += w
+    return wins
+
+
+def check_parity(c: Ctx, shard_global: np.ndarray, shard_local: np.ndarray, d_out, label: str) -> int:
+    """Byte-compare windows of this rank's OUTPUT (after one ciphering pass) with the CPU oracle.
+    shard_global carries offsets / jumped keys in the full set (what the plaintext generator and the
+    oracle need), shard_local the same pieces rebased to this rank's buffers."""
+    import oracle
+    rng = np.random.default_rng(1234 + c.rank)
+    have_ref = oracle.have_ref()
+    checked = 0
+    for i, pos, n in parity_windows(shard_local, PARITY_TARGET, rng):
+        g, l = shard_global[i], shard_local[i]
+        plain = synth.payload(int(g["src_off"]) + pos, n)
+        key = int(g["key"])
+        want = oracle.cycle_at(plain, key, pos)
+        if pos == 0 and have_ref and n <= 8 * MIB:  # stream start: the unmodified reference itself
+            if not np.array_equal(oracle.cycle(plain, key, use_ref=True), want):
+                raise SystemExit(f"ORACLE DISAGREES WITH THE REFERENCE ({label}, piece {i})")
+        o = int(l["dst_off"]) + pos
+        got = d_out[o:o + n].cpu().numpy()
+        if not np.array_equal(got, want):
+            bad = int(np.flatnonzero(got != want)[0])
+            raise SystemExit(f"PARITY FAILURE ({label}): rank {c.rank} piece {i} (set offset {int(g['dst_off']) + pos + bad}) "
+                             f"differs from the reference cipher")
+        checked += n
+    return checked
+
+
+def timed_steps(c: Ctx, step, kernel, steps: int, warmup: int):
+    """K steps between two events on the launching stream; `kernel` (the batched launch) is also
+    bracketed per step.  Returns (max-over-ranks ms for K steps, mean kernel ms on this rank, clocks, launches)."""
+    torch, mb = c.torch, c.mb
+    for _ in range(max(warmup, 3)):
+        step(None)
+    c.barrier()
+    clocks = ClockSampler(c.local)
+    launches0 = mb.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    c.barrier()
+    clocks.start()
+    ev0.record(c.stream)
+    for i in range(steps):
+        step(kev[i])
+    ev1.record(c.stream)
+    torch.cuda.synchronize()
+    info = clocks.stop()
+    launches = mb.launch_count() - launches0
+    ms_total = c.reduce(ev0.elapsed_time(ev1), "max")
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    return ms_total, kernel_ms, info, launches
+
+
+def sustained(c: Ctx, kernel, payload: int, kernel_ms: float, seconds: float = 3.0) -> dict:
+    """>= `seconds` of back-to-back launches of the dominant kernel, with NVML samples."""
+    torch = c.torch
+    iters = max(10, int(seconds * 1e3 / max(kernel_ms, 1e-3)) + 1)
+    clocks = ClockSampler(c.local, period_s=0.02)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    clocks.start()
+    a.record(c.stream)
+    for _ in range(iters):
+        kernel()
+    b.record(c.stream)
+    torch.cuda.synchronize()
+    info = clocks.stop()
+    ms = a.elapsed_time(b) / iters
+    achieved = 2.0 * payload / (ms * 1e-3) / 1e9
+    return {"seconds": a.elapsed_time(b) / 1e3, "launches": iters, "kernel_ms": ms, "achieved": achieved,
+            "frac": achieved / c.peak, "payload_gbs": payload / (ms * 1e-3) / 1e9, "clocks": info}
+
+
+def roofline_block(c: Ctx, payload: int, kernel_ms: float, workload: str, clock_info: dict) -> dict:
+    achieved = 2.0 * payload / (kernel_ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": achieved, "peak": c.peak, "unit": "GB/s", "frac": achieved / c.peak,
+         "traffic": None, "kernel": "modk::cycle_batch_kernel", "kernel_ms": kernel_ms,
+         "algorithmic_bytes_per_launch": 2 * payload, "peak_source": c.peak_src,
+         "payload_gbs": payload / (kernel_ms * 1e-3) / 1e9,
+         "frac_of_nominal_8tbs": achieved / 8000.0}
+    try:  # the co-limiting integer roofline: one IMAD.WIDE per payload byte at the measured issue rate
+        with open(os.path.join(ROOT, "profiles", "imad.json")) as f:
+            lanes = float(json.load(f)["imad_wide_thread_instr_per_clk_per_sm"])
+        sm_count = c.torch.cuda.get_device_properties(c.dev).multi_processor_count
+        mhz = clock_info.get("sm_mhz") or clock_info.get("sm_max_mhz") or 1965.0
+        imad_peak = sm_count * lanes * mhz * 1e6 / 1e9
+        r["imad"] = {"peak_payload_gbs": imad_peak, "frac": r["payload_gbs"] / imad_peak,
+                     "imad_wide_per_clk_per_sm": lanes, "note": "HBM is the binding roofline"}
+    except Exception:
+        pass
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            r["traffic"] = json.load(f).get(workload)
+    except Exception:
+        pass
+    return r
+
+
+def piece_count(descs: np.ndarray, group: int = 16 * MIB) -> int:
+    """Descriptors after the host batch path has cut entries larger than a group (mod_abi.cu batch_host)."""
+    n = descs["len"].astype(np.int64)
+    return int(np.where(n > group + group // 2, np.maximum(1, n // group), 1).sum())
+
+
+def measure_workload(c: Ctx, args, workload: str, *, full: bool, cfg4_n: int = 1_000_000) -> dict:
+    """Device-resident value, per-launch roofline, parity and (if `full`) sustained + e2e for one workload."""
+    torch, mb = c.torch, c.mb
+    gdescs = global_descs(mb, workload, cfg4_n)
+    shard = mb.shard_descs(gdescs, c.rank, c.world) if c.world > 1 else gdescs
+    descs, s0, d0, src_bytes, dst_bytes = rebase(shard)
+    payload = int(descs["len"].sum())
+    in_place = workload in ("cfg3", "cfg4")
+
+    d_src = torch.empty(src_bytes, dtype=torch.uint8, device=c.dev)
+    device_payload(torch, d_src, s0)
+    d_dst = d_src if in_place else torch.empty(dst_bytes, dtype=torch.uint8, device=c.dev)
+    hdr_np = synth.payload(1 << 40, HDR_BYTES)
+    d_hdr = torch.from_numpy(hdr_np).to(c.dev)
+    plan = mb.Plan(descs, src_bytes, dst_bytes)
+    hdr_key = synth.PS4_KEY
+    do_hdr = c.rank == 0
+
+    def kernel():
+        plan.run(d_src.data_ptr(), d_dst.data_ptr(), c.sh)
+
+    def step(ev):
+        if do_hdr:
+            mb.cycle_device(d_hdr.data_ptr() + 4, d_hdr.data_ptr() + 4, HDR_BYTES - 4, hdr_key, c.sh)
+        if ev is not None:
+            ev[0].record(c.stream)
+        kernel()
+        if ev is not None:
+            ev[1].record(c.stream)
+
+    # -- parity, before anything is timed: one pass over the plaintext, windows against the CPU oracle
+    step(None)
+    torch.cuda.synchronize()
+    checked = check_parity(c, shard, descs, d_dst, workload)
+    if do_hdr:
+        import oracle
+        want = hdr_np.copy()
+        want[4:] = oracle.cycle(hdr_np[4:], hdr_key)
+        if not np.array_equal(d_hdr.cpu().numpy(), want):
+            raise SystemExit("PARITY FAILURE: HDR Cycle differs from the reference cipher")
+        checked += HDR_BYTES - 4
+    checked_total = int(c.reduce(float(checked), "sum"))
+    step(None)  # in-place sets: back to plaintext (the cipher is an involution)
+
+    ms_total, kernel_ms, clock_info, launches = timed_steps(c, step, kernel, args.steps, args.warmup)
+    total_payload = int(gdescs["len"].sum())
+    value = (total_payload + (HDR_BYTES - 4)) * args.steps / (ms_total * 1e-3) / 1e9
+    out = {"value": value, "ms_per_step": ms_total / args.steps, "kernel_ms": kernel_ms,
+           "payload_bytes_this_rank": payload, "entries_this_rank": int(len(descs)),
+           "parity_bytes_checked": checked_total, "gpu_launches": int(launches), "clocks": clock_info,
+           "roofline": roofline_block(c, payload, kernel_ms, workload, clock_info),
+           "config": config_block(workload, gdescs, c.world)}
+    if args.kernel_only:
+        return out
+    if full:
+        out["roofline"]["sustained"] = sustained(c, kernel, payload, kernel_ms)
+        c.barrier()
+
+    # -- end to end through the public C ABI with HOST (pinned) buffers: H2D + kernels + D2H per step
+    if full:
+        h_src = torch.empty(src_bytes, dtype=torch.uint8).pin_memory()
+        if (workload in ("cfg3", "cfg4")) and (int(args.steps) % 2 == 1 or True):
+            device_payload(torch, d_src, s0)  # whatever parity the timed loop left: start from plaintext
+        h_src.copy_(d_src)
+        h_dst = h_src if in_place else torch.empty(dst_bytes, dtype=torch.uint8).pin_memory()
+        h_hdr = torch.from_numpy(hdr_np.copy()).pin_memory()
+        del d_src, d_dst, plan
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            if do_hdr:
+                mb.cycle(h_hdr.data_ptr() + 4, HDR_BYTES - 4, hdr_key)
+            mb.cycle_batch(descs, h_src.data_ptr(), h_dst.data_ptr(), src_bytes, dst_bytes)
+
+        e2e_step()  # warm-up 1 doubles as the e2e parity pass: host output against the oracle
+        h_out = h_dst.numpy()
+        import oracle
+        rng = np.random.default_rng(99 + c.rank)
+        e2e_checked = 0
+        for i, pos, n in parity_windows(descs, 16 * MIB, rng):
+            g, l = shard[i], descs[i]
+            want = oracle.cycle_at(synth.payload(int(g["src_off"]) + pos, n), int(g["key"]), pos)
+            o = int(l["dst_off"]) + pos
+            if not np.array_equal(h_out[o:o + n], want):
+                raise SystemExit(f"PARITY FAILURE (e2e {workload}): rank {c.rank} piece {i}")
+            e2e_checked += n
+        e2e_step()  # warm-up 2 (in-place sets: back to plaintext)
+        e2e_steps = max(2, min(args.steps, 4))
+        c.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
         torch.cuda.synchronize()
-        checked = 0
-        sample_descs = gdescs[:setup["n"]]
-        d_lo = int(sample_descs["dst_off"].min())
-        d_hi = int((sample_descs["dst_off"] + sample_descs["len"]).max())
-        got = d_dst[d_lo:d_hi].cpu().numpy()
-        for p, d in zip(setup["parts"], sample_descs):
-            o, l, do = int(p["off"]), int(p["len"]), int(d["dst_off"]) - d_lo
-            if not np.array_equal(got[do:do + l], work[o:o + l]):
-                raise SystemExit(f"PARITY FAILURE: GPU output differs from the reference cipher at entry src_off={o}")
-            checked += l
-        cpu = {"value": setup["bytes"] / secs / 1e9, "unit": "GB/s", "cores": setup["cores"], "kind": setup["kind"],
-               "sample": f"first {setup['n']} entries ({setup['bytes']} payload bytes) of the archive, best of 3; "
-                         f"1-thread rate {setup['rate1'] / 1e9:.3f} GB/s",
-               "gpu_bytes_checked_against_it": checked}
+        e2e_s = c.reduce(time.perf_counter() - t0, "max")
+        out["e2e"] = {"value": (total_payload + (HDR_BYTES - 4)) * e2e_steps / e2e_s / 1e9, "unit": "GB/s",
+                      "h2d_bytes_per_step": payload + (HDR_BYTES - 4 if do_hdr else 0) + piece_count(descs) * 32,
+                      "d2h_bytes_per_step": payload + (HDR_BYTES - 4 if do_hdr else 0),
+                      "steps": e2e_steps, "api": "mod_cycle + mod_cycle_batch on pinned host buffers, one process per GPU",
+                      "parity_bytes_checked": int(c.reduce(float(e2e_checked), "sum"))}
+        ceiling = pcie_ceiling(c.world)
+        if ceiling:
+            out["e2e"]["copy_ceiling_gbs"] = ceiling
+            out["e2e"]["frac_of_copy_ceiling"] = out["e2e"]["value"] / ceiling
+        del h_src, h_dst
+    return out
+
+
+def pcie_ceiling(world: int):
+    """Raw duplex pinned-copy ceiling (payload GB/s with one H2D and one D2H stream per GPU running at
+    once) measured by tools/pcie_probe.py on this pool and committed in profiles/pcie.json."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "pcie.json")) as f:
+            return float(json.load(f)["duplex_payload_gbs"][str(world)])
+    except Exception:
+        return None
+
+
+def inprocess_e2e(c: Ctx, args) -> dict:
+    """The same 16 GiB set through the IN-PROCESS multi-GPU entry point (mod_cycle_batch_sharded: one host
+    thread + stream set per device inside this one process), run by rank 0 alone while the other ranks
+    wait.  Reported beside the one-process-per-GPU e2e."""
+    torch, mb = c.torch, c.mb
+    n_dev = min(c.world, mb.device_count())
+    gdescs = global_descs(mb, "cfg3")
+    total = int(gdescs["len"].sum())
+    h = torch.empty(total, dtype=torch.uint8).pin_memory()
+    h.zero_()
+    mask = (1 << n_dev) - 1
+    p = h.data_ptr()
+    mb.cycle_batch_sharded(gdescs, p, p, total, total, mask)  # warm-up + parity (zero plaintext -> keystream)
+    import oracle
+    hv = h.numpy()
+    for k in (0, 7, 31):
+        o = k * PART + 12345
+        if not np.array_equal(hv[o:o + 65536], oracle.cycle_at(np.zeros(65536, np.uint8), int(gdescs[k]["key"]), 12345)):
+            raise SystemExit("PARITY FAILURE (in-process sharded e2e)")
+    mb.cycle_batch_sharded(gdescs, p, p, total, total, mask)
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        mb.cycle_batch_sharded(gdescs, p, p, total, total, mask)
+    dt = time.perf_counter() - t0
+    return {"value": total * reps / dt / 1e9, "unit": "GB/s", "devices": n_dev, "steps": reps,
+            "api": "mod_cycle_batch_sharded on one pinned host buffer, ONE process driving all devices"}
+
+
+def run_gpu_arm(args) -> None:
+    c = Ctx()
+    if c.world != args.gpus and not (c.world == 1 and args.gpus == 1):
+        if c.world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+    main = measure_workload(c, args, args.workload, full=True)
+    extra = {}
+    if not args.kernel_only and not args.no_extras:
+        if c.world > 1 and args.workload == "cfg3":
+            c.barrier()
+            if c.rank == 0:
+                try:
+                    extra["e2e_inprocess"] = inprocess_e2e(c, args)
+                except SystemExit:
+                    raise
+                except Exception as exc:  # reported, never fatal for the headline line
+                    extra["e2e_inprocess"] = {"error": repr(exc)[:200]}
+            c.barrier()
+        if c.world == 1:
+            for w in ("cfg2", "cfg4"):
+                if w != args.workload:
+                    sub_args = argparse.Namespace(**vars(args))
+                    sub_args.steps = max(5, min(args.steps, 20))
+                    r = measure_workload(c, sub_args, w, full=False)
+                    extra[w] = {k: r[k] for k in ("value", "ms_per_step", "kernel_ms", "parity_bytes_checked",
+                                                  "roofline", "config", "gpu_launches")}
+    if c.rank != 0:
+        c.finish()
+        return
+
+    # -- CPU baseline on this box (N == 1 only): the unmodified reference on a bounded sample
+    cpu = None
+    if c.world == 1 and not args.kernel_only:
+        import oracle
+        os.sched_setaffinity(0, c.all_cpus)  # the CPU baseline uses every host core
+        kind = "reference" if oracle.have_ref() else "port"
+        sample = cpu_sample(global_descs(c.mb, args.workload), args.workload)
+        cores = min(os.cpu_count() or 1, len(sample["parts"]))
+        work = np.empty(sample["bytes"], dtype=np.uint8)
+        cpu_fill_plain(sample, work)
+        cpu_step(sample, work, cores, kind)
+        secs = min(cpu_step(sample, work, cores, kind) for _ in range(3))
+        cpu = {"value": sample["bytes"] / secs / 1e9, "unit": "GB/s", "cores": cores if kind == "reference" else 1,
+               "kind": kind, "sample": sample["sample"] + ", best of 3"}
 
     line = {
-        "metric": "ark_dtb_decrypt_throughput", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_total_max / args.steps, "higher_is_better": True,
-        "scaling": "strong" if in_place else "weak", "vs_baseline": None, "dtype": "u8",
-        "data": "synthetic (all-zero payload; throughput is data-independent)" if in_place else "synthetic",
-        "config": {"workload": args.workload, "entries_per_gpu": int(len(descs)), "payload_bytes_per_gpu": payload,
-                   "layout": ("32 parts x 512 MiB, one (offset, len, key) per part, ciphered in place, "
-                              "HDR Cycle + one batched launch per step") if in_place else
-                             ("byte-packed source entries, 16-byte-aligned extract slots, per-entry keys, "
-                              "HDR Cycle + one batched launch per step"),
-                   "l2": "inputs (>= 1 GiB read + written per step) exceed the 126 MB L2; no flush needed",
-                   "sharding": "mod_shard_descs offset ranges, no collective" if world > 1 else "single GPU",
-                   "host": "rank pinned to its GPU's NUMA-local CPUs (NVML affinity)" if numa_pinned else "default CPU affinity"},
-        "roofline": roofline, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "mod_cycle + mod_cycle_batch on pinned host buffers"},
-        "gpu_launches": int(launches), "clocks": clock_info,
+        "metric": METRIC, "value": main["value"], "unit": "GB/s", "n_gpus": c.world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic (counter-based splitmix64 payload generated on the device; identical to tests/synth.py)",
+        "config": main["config"],
+        "parity_bytes_checked": main["parity_bytes_checked"],
+        "roofline": main["roofline"], "cpu_baseline": cpu,
+        "e2e": main.get("e2e"),
+        "gpu_launches": main["gpu_launches"], "clocks": main["clocks"],
+        "host": "rank pinned to its GPU's NUMA-local CPUs (NVML affinity)" if c.numa_pinned else "default CPU affinity",
+        "per_rank": {"payload_bytes": main["payload_bytes_this_rank"], "entries": main["entries_this_rank"],
+                     "kernel_ms": main["kernel_ms"]},
+        "extra": extra,
     }
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    c.finish()
 
 
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3", "cfg4"])
     ap.add_argument("--kernel-only", action="store_true",
-                    help="profiling aid: skip the e2e and CPU-baseline legs (the line then carries nulls)")
+                    help="profiling aid: device-resident legs only (no sustained run, e2e, extras or CPU baseline)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra.cfg2 / extra.cfg4 / in-process blocks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -24,18 +24,8 @@
 #include <vector>
 
 #include "ArkHeader.h"
+#include "CDtaFile.h"  // SSongConfig, like the reference (CArk.h:6)
 #include "Error.h"
-
-// Same fields as the reference's SSongConfig (CDtaFile.h:25-34); only mPath is consulted on this path.
-struct SSongConfig {
-    std::string mId = "";
-    std::string mName = "";
-    std::string mUnlockMethod = "";
-    std::string mType = "";
-    std::string mPath = "";
-    std::string mArena = "";
-    int miUnlockCount = -1;
-};
 
 class CArk
 {

@@ -1,5 +1,7 @@
 #include "CDtaFile.h"
 
+#include <algorithm>
+#include <cctype>
 #include <cstdio>
 #include <cstring>
 
@@ -227,6 +229,75 @@ SDtaNode* CDtaFile::FindNode(const std::string& lName)
         if (SDtaNode* lpFound = lpTree->FindNode(lName))
             return lpFound;
     return nullptr;
+}
+
+std::vector<SSongConfig> CDtaFile::GetSongs() const
+{
+    std::vector<SSongConfig> laSongs;
+    const SDtaNode* lpTokens = FindNode("unlock_tokens");
+    if (!lpTokens || !lpTokens->mpParent)
+        return laSongs;
+    for (const auto& lpSongNode : lpTokens->mpParent->maChildren) {
+        // {id, name, unlock title, unlock description, icon, type}
+        if (!lpSongNode->IsTree() || lpSongNode->maChildren.size() != 6)
+            continue;
+        const SDtaNode& lId = *lpSongNode->maChildren[0];
+        const SDtaNode& lName = *lpSongNode->maChildren[1];
+        if (!lId.IsString() || !lName.IsString())
+            continue;
+        // songs are the records whose id has no lower-case letter
+        if (std::any_of(lId.mString.begin(), lId.mString.end(), [](char c) { return c != (char)std::toupper(c); }))
+            continue;
+        SSongConfig lConfig;
+        lConfig.mId = lId.mString;
+        lConfig.mName = lName.mString;
+        laSongs.push_back(lConfig);
+    }
+    const SDtaNode* lpCampaign = FindNode("campaign");
+    if (!lpCampaign || !lpCampaign->mpParent)
+        return laSongs;
+    for (const auto& lpUnlockNode : lpCampaign->mpParent->maChildren) {
+        // {method, count, type, unlocked item id}
+        if (!lpUnlockNode->IsTree() || lpUnlockNode->maChildren.size() != 4)
+            continue;
+        const SDtaNode& lMethod = *lpUnlockNode->maChildren[0];
+        const SDtaNode& lCount = *lpUnlockNode->maChildren[1];
+        const SDtaNode& lItem = *lpUnlockNode->maChildren[3];
+        if (!lMethod.IsString() || !lCount.IsInteger() || !lItem.IsString())
+            continue;
+        for (SSongConfig& lSong : laSongs) {
+            if (lSong.mId == lItem.mString) {
+                lSong.mUnlockMethod = lMethod.mString;
+                lSong.miUnlockCount = lCount.miValue;
+            }
+        }
+    }
+    return laSongs;
+}
+
+void CDtaFile::GetSongData(std::vector<SSongConfig>& laSongs) const
+{
+    for (SSongConfig& lSong : laSongs) {
+        const SDtaNode* lpIdNode = FindNode(lSong.mId);
+        if (!lpIdNode)
+            continue;
+        const SDtaNode* lpSongNode = lpIdNode->mpParent;  // {id, path, (type <type>)}
+        if (!lpSongNode || lpSongNode->maChildren.size() < 3)
+            continue;
+        const SDtaNode* lpArenaNode = lpSongNode->mpParent;
+        if (lpArenaNode && !lpArenaNode->maChildren.empty() && lpArenaNode->maChildren[0]->IsString())
+            lSong.mArena = lpArenaNode->maChildren[0]->mString;
+        const SDtaNode& lPath = *lpSongNode->maChildren[1];
+        if (!lPath.IsString())
+            continue;
+        lSong.mPath = lPath.mString;
+        std::transform(lSong.mPath.begin(), lSong.mPath.end(), lSong.mPath.begin(),
+                       [](unsigned char c) { return (char)std::tolower(c); });
+        const SDtaNode& lTypeTree = *lpSongNode->maChildren[2];
+        if (lTypeTree.maChildren.size() < 2 || !lTypeTree.maChildren.back()->IsString())
+            continue;
+        lSong.mType = lTypeTree.maChildren.back()->mString;
+    }
 }
 
 bool CDtaFile::SetIntAfter(const std::string& lKey, int32_t liValue)

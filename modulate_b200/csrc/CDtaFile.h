@@ -13,10 +13,11 @@
 //     16 / 17         i32 (written as 1), tree      (two sub-tree flavours)
 //   further top-level trees follow as: i32 type (16 | 17), i32, tree
 //
-// Same class name and Load/Save signatures as the reference (CDtaFile.h:169-188); the song-list
-// editing commands built on top of it there (GetSongs / SetSongs / ...) are tool policy outside the
-// scope of this repo.  The node model here is a tagged value tree, not the reference's class
-// hierarchy.
+// Same class name and Load/Save signatures as the reference (CDtaFile.h:169-188), plus the two
+// read-only song queries `-pack` depends on (GetSongs / GetSongData, CDtaFile.cpp:102-181, :248-294:
+// they decide which /songs/ folders a repack keeps).  The song-list EDITING commands (SetSongs,
+// RemoveSong, UpdateSongData) are tool policy outside the scope of this repo.  The node model here
+// is a tagged value tree, not the reference's class hierarchy.
 #pragma once
 
 #include <cstdint>
@@ -39,6 +40,17 @@ enum eNodeType {
     ENodeType_IncludeFile = 33,
     ENodeType_Define = 35,
     ENodeType_Invalid
+};
+
+// Same fields as the reference's SSongConfig (CDtaFile.h:25-34).
+struct SSongConfig {
+    std::string mId = "";
+    std::string mName = "";
+    std::string mUnlockMethod = "";
+    std::string mType = "";
+    std::string mPath = "";
+    std::string mArena = "";
+    int miUnlockCount = -1;
 };
 
 struct SDtaNode {
@@ -79,6 +91,15 @@ public:
     std::vector<std::unique_ptr<SDtaNode>>& Trees() { return maTrees; }
     const std::vector<std::unique_ptr<SDtaNode>>& Trees() const { return maTrees; }
     SDtaNode* FindNode(const std::string& lName);
+    const SDtaNode* FindNode(const std::string& lName) const { return const_cast<CDtaFile*>(this)->FindNode(lName); }
+
+    // The songs amp_config lists (ids in upper case, six-field records next to "unlock_tokens") with
+    // their unlock data (four-field records next to "campaign"): reference CDtaFile.cpp:102-181.
+    // Where the reference dereferences a null pointer on a config without those nodes, this returns
+    // an empty list.
+    std::vector<SSongConfig> GetSongs() const;
+    // Fill mPath (lower-cased), mArena and mType of each song from amp_songs_config: CDtaFile.cpp:248-294.
+    void GetSongData(std::vector<SSongConfig>& laSongs) const;
 
     // Convenience for host-side patches: the value that FOLLOWS the string node `lKey` inside its
     // parent tree, i.e. the `(key value)` idiom of DTA.  Returns false if there is no such pair.

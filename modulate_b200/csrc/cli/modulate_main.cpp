@@ -1,7 +1,8 @@
 // modulate_main.cpp -- portable command line over the facade: the reference's archive commands
 // (-ps3 -verbose -force -packall -unpack -pack -pack_add -decode; Modulate.cpp:45-70, :291-317,
-// :380-502, :895-972) with the same left-to-right command deque and exit convention.  The song /
-// DTA commands of the reference are host-side tooling outside the hot path and are not provided.
+// :380-502, :895-972) with the same left-to-right command deque and exit convention.  -pack reads
+// the song list from the DTA configs like the reference; the song-list EDITING commands of the
+// reference are host-side tooling outside the hot path and are not provided.
 //
 // Extensions: -bodykey K (cipher every entry body with key K, stream restarting per entry -- the
 // synthetic per-entry-key configurations), -device N (bind GPU N).
@@ -124,13 +125,27 @@ eError PackImpl(std::deque<std::string>& laParams)
     WithSlash(lInputPath);
     WithSlash(lOutputPath);
 
-    // The reference derives the song list from the DTA configs unless -packall is given
-    // (Modulate.cpp:410-432); that DTA tooling is out of scope here, so the list is empty and the
-    // /songs/ filter keeps only the four built-in songs unless -packall.
+    // Unless -packall is given the song list comes from the two DTA configs inside the input tree,
+    // like the reference (Modulate.cpp:410-432): it decides which /songs/<name>/ folders are packed.
+    eError leError = eError_NoError;
     std::vector<SSongConfig> lSongs;
+    if (!CSettings::mbPackAllFiles) {
+        const std::string lPlatform = CSettings::msPlatform;
+        const std::string lAmpConfigPath = lInputPath + lPlatform + "/config/amp_config.dta_dta_" + lPlatform;
+        std::cout << "Loading " << lAmpConfigPath << "\n";
+        CDtaFile lAmpConfig;
+        leError = lAmpConfig.Load(lAmpConfigPath.c_str());
+        SHOW_ERROR_AND_RETURN;
+        lSongs = lAmpConfig.GetSongs();
+        CDtaFile lSongsConfig;
+        const std::string lAmpSongsConfigPath = lInputPath + lPlatform + "/config/amp_songs_config.dta_dta_" + lPlatform;
+        leError = lSongsConfig.Load(lAmpSongsConfigPath.c_str());
+        SHOW_ERROR_AND_RETURN;
+        lSongsConfig.GetSongData(lSongs);
+    }
 
     CArk lReferenceArkHeader;
-    eError leError = lReferenceArkHeader.Load(HeaderName().c_str());
+    leError = lReferenceArkHeader.Load(HeaderName().c_str());
     SHOW_ERROR_AND_RETURN;
 
     CArk lArkHeader;
@@ -185,6 +200,39 @@ eError Decode(std::deque<std::string>&)
     return liWritten == lData.size() ? eError_NoError : eError_FailedToWriteData;
 }
 
+// -listsongs <dir>: the reference's read-only song listing (Modulate.cpp:504-547), same output format.
+eError ListSongs(std::deque<std::string>& laParams)
+{
+    std::cout << "Loading ";
+    if (laParams.empty())
+        return eError_InvalidParameter;
+    std::string lBasePath = laParams.front();
+    laParams.pop_front();
+    WithSlash(lBasePath);
+    const std::string lPlatform = CSettings::msPlatform;
+    const std::string lAmpConfigPath = lBasePath + lPlatform + "/config/amp_config.dta_dta_" + lPlatform;
+    std::cout << lAmpConfigPath << "\n";
+    CDtaFile lAmpConfig;
+    eError leError = lAmpConfig.Load(lAmpConfigPath.c_str());
+    SHOW_ERROR_AND_RETURN;
+    const std::string lAmpSongsConfigPath = lBasePath + lPlatform + "/config/amp_songs_config.dta_dta_" + lPlatform;
+    std::cout << "Loading " << lAmpSongsConfigPath << "\n";
+    CDtaFile lSongsConfig;
+    leError = lSongsConfig.Load(lAmpSongsConfigPath.c_str());
+    SHOW_ERROR_AND_RETURN;
+    std::cout << "\n";
+    int ii = 1;
+    std::vector<SSongConfig> lSongs = lAmpConfig.GetSongs();
+    lSongsConfig.GetSongData(lSongs);
+    for (const SSongConfig& lSong : lSongs) {
+        std::cout << "Song " << ii << "\t  " << lSong.mId << " - " << lSong.mName << " - " << lSong.mType << "\n\t  "
+                  << lSong.mPath << "\n\t  Unlocked by " << lSong.mUnlockMethod << " " << lSong.miUnlockCount << "\n"
+                  << "\t  Arena: " << lSong.mArena << "\n\n";
+        ++ii;
+    }
+    return eError_NoError;
+}
+
 // -dtaset <file> <key> <value>: load a binary DTA file, replace the value that follows the symbol
 // <key> (integer or string, whichever is there) and save it back -- the host-side patch step of a
 // repack.  -dtacopy <in> <out>: load + save (codec round trip).
@@ -234,6 +282,7 @@ void PrintUsage()
               << "  -pack <in_dir> <out_dir>    Repack the files the reference header knows\n"
               << "  -pack_add <in_dir> <out_dir> Repack, also adding new files\n"
               << "  -decode                     Write the deciphered header to main_<platform>.hdr.dec\n"
+              << "  -listsongs <dir>            List the songs the DTA configs under <dir> define\n"
               << "  -dtaset <file> <key> <val>  Patch the value following symbol <key> in a binary DTA file\n"
               << "  -dtacopy <in> <out>         Load and re-save a binary DTA file\n";
 }
@@ -250,6 +299,7 @@ int main(int argc, char* argv[])
         {"-ps3", PS3},       {"-verbose", EnableVerbose}, {"-force", EnableForceWrite}, {"-packall", EnablePackAll},
         {"-bodykey", BodyKey}, {"-device", Device},       {"-unpack", Unpack},          {"-pack", Pack},
         {"-pack_add", AddPack}, {"-decode", Decode},   {"-dtaset", DtaSet},          {"-dtacopy", DtaCopy},
+        {"-listsongs", ListSongs},
     };
 
     std::deque<std::string> laParams;

@@ -49,16 +49,20 @@ using modlcg::low8_canonical;
 #define MODK_CANON_FMA_MASK 0x5  // exact path: which of every 4 bytes canonicalise on the FMA pipe (IMAD.HI) vs ALU (LEA.HI)
 #endif
 #ifndef MODK_MIN_CTAS
-#define MODK_MIN_CTAS 8          // batched kernel: resident CTAs per SM requested through __launch_bounds__ (64 registers)
+#define MODK_MIN_CTAS 8          // GENERAL kernels (any source alignment): resident CTAs per SM (64 registers)
+#endif
+#ifndef MODK_MIN_CTAS_COAL
+#define MODK_MIN_CTAS_COAL 10    // CO-ALIGNED kernels (source and destination agree mod 16, e.g. in place): 48 registers
+#endif
+#ifndef MODK_STAGE
+#define MODK_STAGE 1             // general kernels: 1 = the tile's source span is staged through shared memory by ONE
+                                 // bulk-async copy per CTA (cp.async.bulk + mbarrier), 0 = two LDG.128 per chunk into registers
 #endif
 #ifndef MODK_HOIST_POW
 #define MODK_HOIST_POW 1         // batched kernel: request the jump factors before the tile record arrives
 #endif
 #ifndef MODK_REC_PREFETCH
 #define MODK_REC_PREFETCH 2048   // batched kernel: L2 prefetch distance for tile records, in tiles (0 = off)
-#endif
-#ifndef MODK_MIN_CTAS_INLINE
-#define MODK_MIN_CTAS_INLINE 8   // contiguous kernel: resident CTAs per SM
 #endif
 
 // tile index within an entry < 2^32 / kTileBytes + 1; split 10 bits low / rest high
@@ -83,6 +87,52 @@ __device__ __forceinline__ void stg128(uint64_t addr, const uint4& v)
 {
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
+
+#if MODK_STAGE
+// ---- bulk-async staging: mbarrier + cp.async.bulk (SASS: UBLKCP / SYNCS) --------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MODK_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MODK_DONE;\n"
+        "bra MODK_WAIT;\n"
+        "MODK_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// global -> shared bulk copy of `bytes` (multiple of 16, both addresses 16-byte aligned); completion
+// is signalled on the mbarrier as transaction bytes
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, uint64_t src_gmem, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src_gmem), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+#endif
 
 // ---- per-chunk arithmetic -------------------------------------------------------------------
 
@@ -167,23 +217,28 @@ __device__ __noinline__ void slow_chunk(uint64_t src_byte0, uint64_t dst_chunk, 
 // independent 16-step chains interleave.
 // kWs < 0: source and destination are co-aligned (one load per chunk).  kWs in 0..3: the chunk
 // starts kWs words (+ `bs` / 8 bytes) into its first granule and straddles two.
-template <int kWs, int U>
+// kStaged: the tile's source span has been requested into shared memory by one bulk-async copy
+// (issued by thread 0 in run_tile); the granules are read from there AFTER the keystream has been
+// generated, so no register holds a load in flight.
+template <int kWs, int U, bool kStaged>
 __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint64_t dst_tile, const uint32_t st,
                                              const uint32_t n_valid, const uint32_t head, const uint32_t tail,
                                              const uint32_t bs, const uint32_t idx0, const uint32_t (&pw)[U],
-                                             const uint32_t two)
+                                             const uint32_t two, const uint32_t stage, const uint32_t bar)
 {
     constexpr uint32_t T = (uint32_t)kThreadsPerCta;
     uint4 own[U], nxt[U];
     const uint64_t sp = src_tile + 16ull * idx0;
+    if (!kStaged) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        own[u] = make_uint4(0u, 0u, 0u, 0u);
-        nxt[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (idx0 + (uint32_t)u * T < n_valid) {
-            own[u] = ldg128(sp + 16ull * T * u);
-            if (kWs >= 0)
-                nxt[u] = ldg128(sp + 16ull * T * u + 16ull);
+        for (int u = 0; u < U; ++u) {
+            own[u] = make_uint4(0u, 0u, 0u, 0u);
+            nxt[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (idx0 + (uint32_t)u * T < n_valid) {
+                own[u] = ldg128(sp + 16ull * T * u);
+                if (kWs >= 0)
+                    nxt[u] = ldg128(sp + 16ull * T * u + 16ull);
+            }
         }
     }
 
@@ -223,6 +278,22 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
 #endif
     const bool redo = (any & 0x80800000u) != 0u;
 
+#if MODK_STAGE
+    if (kStaged) {
+        mbar_wait(bar, 0u);  // the CTA's only use of the barrier: phase 0
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            own[u] = make_uint4(0u, 0u, 0u, 0u);
+            nxt[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (idx0 + (uint32_t)u * T < n_valid) {
+                own[u] = lds128(stage + 16u * (idx0 + (uint32_t)u * T));
+                if (kWs >= 0)
+                    nxt[u] = lds128(stage + 16u * (idx0 + (uint32_t)u * T) + 16u);
+            }
+        }
+    }
+#endif
+
     const uint32_t f_lo = head ? 1u : 0u;
     const uint32_t f_hi = max(n_valid - (tail < 16u ? 1u : 0u), f_lo);
     const uint64_t dp = dst_tile + 16ull * idx0;
@@ -248,10 +319,14 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
     }
 }
 
-template <int U>
+// kGeneral = false: the launch guarantees that source and destination agree mod 16 (in-place runs, co-aligned
+// copies): one LDG.128 per chunk straight into registers, no re-alignment code in the kernel at all.
+// kGeneral = true: any alignment; the tile's source span comes through shared memory (MODK_STAGE) or as two
+// LDG.128 per chunk, and a funnel shift re-aligns it.
+template <int U, bool kGeneral>
 __device__ __forceinline__ void run_tile(const BatchArgs& a, const int64_t src_rel, const int64_t dst_rel,
                                          const uint32_t st, const uint32_t geom, const uint32_t idx0,
-                                         const uint32_t (&pw)[U])
+                                         const uint32_t (&pw)[U], const uint32_t stage, const uint32_t bar)
 {
     const uint64_t dst_tile = (uint64_t)a.dst + (uint64_t)dst_rel;
     const uint64_t sv = (uint64_t)a.src + (uint64_t)src_rel;  // source address that pairs with chunk 0, byte 0
@@ -259,9 +334,10 @@ __device__ __forceinline__ void run_tile(const BatchArgs& a, const int64_t src_r
     const uint64_t src_tile = sv - shift;
     const uint32_t n_valid = geom & 0xFFFu, head = (geom >> 12) & 15u, tail = (geom >> 16) & 31u;
 
-    // whole-granule loads are allowed only inside the source buffer (CTA-uniform test)
+    // whole-granule loads are allowed only inside the source buffer (CTA-uniform test); a misaligned
+    // tile in a co-aligned launch (the host never produces one) also lands here and stays correct
     const uint64_t src_end = src_tile + 16ull * (n_valid + (shift ? 1u : 0u));
-    if (__builtin_expect(src_tile < a.src_lo16 || src_end > a.src_hi16, 0)) {
+    if (__builtin_expect(src_tile < a.src_lo16 || src_end > a.src_hi16 || (!kGeneral && shift != 0u), 0)) {
 #pragma unroll 1
         for (int u = 0; u < U; ++u) {
             const uint32_t idx = idx0 + (uint32_t)u * (uint32_t)kThreadsPerCta;
@@ -273,14 +349,26 @@ __device__ __forceinline__ void run_tile(const BatchArgs& a, const int64_t src_r
     }
 
     const uint32_t bs = (shift & 3u) * 8u;
+    if (!kGeneral) {
+        process_tile<-1, U, false>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar);
+        return;
+    }
+    constexpr bool kStaged = MODK_STAGE != 0;
+#if MODK_STAGE
+    if (threadIdx.x == 0) {  // one bulk-async copy brings the tile's whole source span into shared memory
+        const uint32_t bytes = 16u * (n_valid + (shift ? 1u : 0u));
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(stage, src_tile, bytes, bar);
+    }
+#endif
     if (shift == 0u) {
-        process_tile<-1, U>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two);
+        process_tile<-1, U, kStaged>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar);
     } else {
         switch (shift >> 2) {
-        case 0: process_tile<0, U>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two); break;
-        case 1: process_tile<1, U>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two); break;
-        case 2: process_tile<2, U>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two); break;
-        default: process_tile<3, U>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two); break;
+        case 0: process_tile<0, U, kStaged>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar); break;
+        case 1: process_tile<1, U, kStaged>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar); break;
+        case 2: process_tile<2, U, kStaged>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar); break;
+        default: process_tile<3, U, kStaged>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar); break;
         }
     }
 }
@@ -314,6 +402,24 @@ __device__ __forceinline__ TileRec make_tile_rec(uint64_t src_off, uint64_t dst_
     return r;
 }
 
+// Shared-memory stage + its mbarrier (general kernels only): initialised by thread 0 while the tile
+// record is still in flight; used for exactly one phase, the CTA then retires.
+#if MODK_STAGE
+#define MODK_STAGE_SETUP                                                                          \
+    uint32_t stage = 0u, bar = 0u;                                                                \
+    if (kGeneral) {                                                                               \
+        __shared__ __align__(128) uint8_t s_stage[kTileBytes + 16];                               \
+        __shared__ __align__(8) uint64_t s_bar;                                                   \
+        stage = smem_u32(s_stage);                                                                \
+        bar = smem_u32(&s_bar);                                                                   \
+        if (threadIdx.x == 0)                                                                     \
+            mbar_init(bar, 1u);                                                                   \
+        __syncthreads();                                                                          \
+    }
+#else
+#define MODK_STAGE_SETUP const uint32_t stage = 0u, bar = 0u;
+#endif
+
 // This thread's jump factors a^(16 * chunk): they depend on nothing but the thread index, so they are
 // requested before (and fly together with) the tile record.
 template <int U>
@@ -328,8 +434,11 @@ __device__ __forceinline__ void load_chunk_pows(uint32_t (&pw)[U], uint32_t idx0
 // lives for ~3 us, so the DRAM latency of its own record would be a large part of its life: every
 // CTA therefore pulls the 128-byte line holding the records of the CTAs MODK_REC_PREFETCH tiles
 // further on (about two waves of resident CTAs) into L2.
-__global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_kernel(const BatchArgs a)
+template <bool kGeneral>
+__global__ void __launch_bounds__(kThreadsPerCta, kGeneral ? MODK_MIN_CTAS : MODK_MIN_CTAS_COAL)
+cycle_batch_kernel(const BatchArgs a)
 {
+    MODK_STAGE_SETUP
     const uint4* p = reinterpret_cast<const uint4*>(a.tiles + blockIdx.x);
     uint32_t pw[kUnroll];
 #if MODK_HOIST_POW
@@ -349,16 +458,18 @@ __global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS) cycle_batch_ker
 #if !MODK_HOIST_POW
     load_chunk_pows<kUnroll>(pw, threadIdx.x);
 #endif
-    run_tile<kUnroll>(a, src_rel, dst_rel, hi.x, hi.y, threadIdx.x, pw);
+    run_tile<kUnroll, kGeneral>(a, src_rel, dst_rel, hi.x, hi.y, threadIdx.x, pw, stage, bar);
 }
 
 // Same kernel with the (few) descriptors in the parameter block: nothing to upload, nothing to
 // allocate, so a contiguous Cycle() is a single asynchronous launch.  The tile record is computed
 // from the constant-bank jump tables instead of being loaded.  (A short buffer such as the 384 KiB
 // HDR is 48 CTAs that all run at once, each thread's 4 chains interleaved: one chain latency.)
-__global__ void __launch_bounds__(kThreadsPerCta, MODK_MIN_CTAS_INLINE)
+template <bool kGeneral>
+__global__ void __launch_bounds__(kThreadsPerCta, kGeneral ? MODK_MIN_CTAS : MODK_MIN_CTAS_COAL)
 cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
 {
+    MODK_STAGE_SETUP
     uint32_t pw[kUnroll];
     load_chunk_pows<kUnroll>(pw, threadIdx.x);
     const uint32_t tile = blockIdx.x;
@@ -366,7 +477,7 @@ cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
     const DevDesc& d = in.d[e];
     const TileRec r = make_tile_rec(d.src_off, d.dst_off, d.len, d.neg_state, tile - d.first_tile,
                                     (uint32_t)(uintptr_t)a.dst & 15u, e);
-    run_tile<kUnroll>(a, r.src_rel, r.dst_rel, r.state, r.geom, threadIdx.x, pw);
+    run_tile<kUnroll, kGeneral>(a, r.src_rel, r.dst_rel, r.state, r.geom, threadIdx.x, pw, stage, bar);
 }
 
 // Plan kernel, one thread per tile: find the tile's entry (the last entry whose first_tile <= tile;
@@ -417,6 +528,15 @@ cudaError_t upload_tables()
 
 constexpr uint32_t kMaxGrid = 0x7FFFFFFFu;  // gridDim.x limit
 
+// Every tile of the launch has source and destination co-aligned mod 16: all entries share one
+// (src_off - dst_off) mod 16 and the two base pointers make up for it.
+static bool coaligned(const BatchArgs& a)
+{
+    if (a.uniform_delta < 0 || getenv("MOD_FORCE_GENERAL") != nullptr)  // (the variable is a test / tuning aid)
+        return false;
+    return (((uintptr_t)a.src - (uintptr_t)a.dst + (uintptr_t)a.uniform_delta) & 15u) == 0u;
+}
+
 cudaError_t launch_batch(const BatchArgs& args, cudaStream_t stream)
 {
     for (uint32_t t0 = 0; t0 < args.n_tiles;) {
@@ -424,7 +544,10 @@ cudaError_t launch_batch(const BatchArgs& args, cudaStream_t stream)
         BatchArgs a = args;
         a.tiles = args.tiles + t0;
         a.n_tiles = n;
-        cycle_batch_kernel<<<n, kThreadsPerCta, 0, stream>>>(a);
+        if (coaligned(args))
+            cycle_batch_kernel<false><<<n, kThreadsPerCta, 0, stream>>>(a);
+        else
+            cycle_batch_kernel<true><<<n, kThreadsPerCta, 0, stream>>>(a);
         const cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess)
             return err;
@@ -437,7 +560,10 @@ cudaError_t launch_batch_inline(const BatchArgs& args, const InlineDescs& descs,
 {
     if (args.n_tiles == 0)
         return cudaSuccess;
-    cycle_inline_kernel<<<args.n_tiles, kThreadsPerCta, 0, stream>>>(args, descs);
+    if (coaligned(args))
+        cycle_inline_kernel<false><<<args.n_tiles, kThreadsPerCta, 0, stream>>>(args, descs);
+    else
+        cycle_inline_kernel<true><<<args.n_tiles, kThreadsPerCta, 0, stream>>>(args, descs);
     return cudaGetLastError();
 }
 

@@ -63,6 +63,9 @@ struct BatchArgs {
     uint64_t src_lo16;
     uint64_t src_hi16;
     uint32_t two = 2;  // the literal 2, kept opaque to ptxas (see low8_canonical_fma)
+    // (src_off - dst_off) & 15 if it is the same for every entry of the launch, else -1: together with
+    // the base pointers it tells the host whether the co-aligned kernel may be used
+    int32_t uniform_delta = -1;
 };
 
 // Number of tiles an entry of `len` bytes occupies when its first destination byte sits at

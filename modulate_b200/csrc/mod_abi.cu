@@ -294,6 +294,7 @@ int launch_contiguous(const uint8_t* d_src, uint8_t* d_dst, uint64_t len, int32_
         args.tiles_per_entry = tpe;
         args.src_lo16 = src_lo16;
         args.src_hi16 = src_hi16;
+        args.uniform_delta = 0;  // src_off == dst_off for every piece
         CUDA_TRY(modk::launch_batch_inline(args, in, stream));
         g_launches.fetch_add(1, std::memory_order_relaxed);
     }
@@ -355,6 +356,22 @@ int validate_descs(const char* who, const mod_desc* descs, uint64_t n, uint64_t 
                         (unsigned long long)i, (unsigned long long)d.dst_off, d.len, (unsigned long long)dst_bytes);
     }
     return MOD_OK;
+}
+
+// (src_off - dst_off) & 15 when every non-empty descriptor agrees on it, else -1.
+int32_t uniform_delta_of(const mod_desc* descs, uint64_t n)
+{
+    int32_t delta = -1;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!descs[i].len)
+            continue;
+        const int32_t d = (int32_t)((descs[i].src_off - descs[i].dst_off) & 15u);
+        if (delta < 0)
+            delta = d;
+        else if (delta != d)
+            return -1;
+    }
+    return delta;
 }
 
 // Expand (already validated) descriptors into device descriptors with their first-tile prefix.
@@ -609,6 +626,7 @@ int batch_host(DeviceCtx& c, const mod_desc* user_descs, uint64_t user_n, const 
     if (e == cudaSuccess)
         e = cudaEventRecord(c.plan_ready, c.pipe_stream[0]);
     const modk::TileRec* d_tiles = (const modk::TileRec*)c.ws_tiles;
+    const int32_t uniform_delta = uniform_delta_of(descs, n);
     const double t_plan = now_ms();
 
     // test hook (tests/test_gpu_multidev.py): pretend the runtime failed at this group, with earlier
@@ -645,6 +663,7 @@ int batch_host(DeviceCtx& c, const mod_desc* user_descs, uint64_t user_n, const 
         args.tiles_per_entry = 0;
         args.src_lo16 = ((uint64_t)(uintptr_t)win_src + 15u) & ~15ull;
         args.src_hi16 = ((uint64_t)(uintptr_t)win_src + (g.s_hi - g.s_lo)) & ~15ull;
+        args.uniform_delta = uniform_delta;
         e = modk::launch_batch(args, s);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (e != cudaSuccess)
@@ -750,6 +769,7 @@ struct mod_plan {
     uint32_t dst_align = 0;
     uint64_t payload = 0;
     uint32_t n_tiles = 0;
+    int32_t uniform_delta = -1;  // (src_off - dst_off) & 15 if all entries agree: selects the co-aligned kernel
     modk::TileRec* d_tiles = nullptr;
     std::vector<mod_desc> descs;        // host copy: window validation, tile ranges
     std::vector<uint32_t> first_tile;   // n + 1 entries
@@ -989,6 +1009,7 @@ int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint6
     p->dst_align = dst_align;
     p->payload = payload;
     p->n_tiles = (uint32_t)tiles;
+    p->uniform_delta = uniform_delta_of(descs, n);
     modk::DevDesc* d_descs = nullptr;  // only needed while the tile records are built
     auto cleanup = [&]() {
         if (d_descs) cudaFree(d_descs);
@@ -1094,6 +1115,7 @@ int mod_plan_run(const mod_plan* plan, const void* d_src, void* d_dst, void* str
     args.tiles_per_entry = 0;
     args.src_lo16 = ((uint64_t)(uintptr_t)d_src + 15u) & ~15ull;
     args.src_hi16 = ((uint64_t)(uintptr_t)d_src + plan->src_bytes) & ~15ull;
+    args.uniform_delta = plan->uniform_delta;
     CUDA_TRY(modk::launch_batch(args, (cudaStream_t)stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return MOD_OK;
@@ -1142,6 +1164,7 @@ int mod_plan_run_window(const mod_plan* plan, uint64_t tile_begin, uint64_t tile
     args.tiles_per_entry = 0;
     args.src_lo16 = ((uint64_t)(uintptr_t)d_src_win + 15u) & ~15ull;
     args.src_hi16 = ((uint64_t)(uintptr_t)d_src_win + src_win_bytes) & ~15ull;
+    args.uniform_delta = plan->uniform_delta;
     CUDA_TRY(modk::launch_batch(args, (cudaStream_t)stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return MOD_OK;

@@ -45,6 +45,47 @@ int ark_ref_construct(void* lpArk, const char* lpInputDirectory, void* lpReferen
 {
     return (int)((CArk*)lpArk)->ConstructFromDirectory(lpInputDirectory, *(const CArk*)lpReferenceHeader, {});
 }
+// Modulate.cpp:410-432 (Pack without -packall): the song list comes from the two DTA configs.
+static eError LoadSongs(const char* lpAmpConfig, const char* lpAmpSongsConfig, std::vector<SSongConfig>& laSongs)
+{
+    CDtaFile lAmpConfig;
+    eError leError = lAmpConfig.Load(lpAmpConfig);
+    if (leError != eError_NoError)
+        return leError;
+    laSongs = lAmpConfig.GetSongs();
+    CDtaFile lSongsConfig;
+    leError = lSongsConfig.Load(lpAmpSongsConfig);
+    if (leError != eError_NoError)
+        return leError;
+    lSongsConfig.GetSongData(laSongs);
+    return eError_NoError;
+}
+
+int ark_ref_construct_with_songs(void* lpArk, const char* lpInputDirectory, void* lpReferenceHeader,
+                                 const char* lpAmpConfig, const char* lpAmpSongsConfig)
+{
+    std::vector<SSongConfig> laSongs;
+    eError leError = LoadSongs(lpAmpConfig, lpAmpSongsConfig, laSongs);
+    if (leError != eError_NoError)
+        return (int)leError;
+    return (int)((CArk*)lpArk)->ConstructFromDirectory(lpInputDirectory, *(const CArk*)lpReferenceHeader, laSongs);
+}
+
+// One line per song: id, name, unlock method, unlock count, path, arena, type (tab separated).
+int dta_ref_songs(const char* lpAmpConfig, const char* lpAmpSongsConfig, char* lpOut, int liCapacity)
+{
+    std::vector<SSongConfig> laSongs;
+    eError leError = LoadSongs(lpAmpConfig, lpAmpSongsConfig, laSongs);
+    if (leError != eError_NoError)
+        return -(int)leError;
+    std::string lText;
+    for (const SSongConfig& lSong : laSongs)
+        lText += lSong.mId + "\t" + lSong.mName + "\t" + lSong.mUnlockMethod + "\t" + std::to_string(lSong.miUnlockCount) + "\t" +
+                 lSong.mPath + "\t" + lSong.mArena + "\t" + lSong.mType + "\n";
+    snprintf(lpOut, (size_t)liCapacity, "%s", lText.c_str());
+    return (int)laSongs.size();
+}
+
 int ark_ref_build(void* lpArk, const char* lpInputDirectory) { return (int)((CArk*)lpArk)->BuildArk(lpInputDirectory, {}); }
 int ark_ref_save(void* lpArk, const char* lpOutputDirectory, const char* lpHeaderFilename)
 {

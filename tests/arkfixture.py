@@ -70,3 +70,63 @@ def read_header(path: str) -> ao.Header:
     magic = int.from_bytes(raw[:4], "little")
     plain = raw[:4] + oracle.cycle(np.frombuffer(raw[4:], dtype=np.uint8), ao.platform_key(magic)).tobytes()
     return ao.parse_header(plain), plain
+
+
+# ---- the two DTA configs `-pack` reads its song list from (reference Modulate.cpp:410-432) -----------------
+
+SONGS = [
+    {"id": "CUSTOM1", "name": "Custom One", "path": "../songs/Custom1/custom1.moggsong", "arena": "World1",
+     "type": "kSongNormal", "unlock_method": "play_num", "unlock_count": 3},
+    {"id": "CREDITS", "name": "Credits", "path": "songs/credits/credits.moggsong", "arena": "World2",
+     "type": "kSongBoss", "unlock_method": "", "unlock_count": -1},
+    {"id": "NOT_IN_SONGS_CONFIG", "name": "Orphan", "path": "", "arena": "", "type": "",
+     "unlock_method": "beat_num", "unlock_count": 7},
+]
+
+
+def song_config_blobs():
+    """(amp_config, amp_songs_config) DTB blobs shaped the way CDtaFile::GetSongs / GetSongData walk them
+    (CDtaFile.cpp:102-181, :248-294): six-field song records beside "unlock_tokens" (ids without lower-case
+    letters are songs), four-field unlock records beside "campaign", {id, path, (type T)} records inside
+    arena groups."""
+    from oracle import dta_oracle as do
+
+    def sym(text, t=5):
+        return ("str", t, text.encode())
+
+    records = [sym("unlock_tokens")]
+    for i, sg in enumerate(SONGS):
+        records.append(("tree", 16, 10 + i, [sym(sg["id"]), sym(sg["name"]), sym("unlock_extra"), sym("unlock_extra_desc"),
+                                             sym("ui/textures/black_square.png"), sym("CAMPVO_song_extra")]))
+    records.append(("tree", 16, 30, [sym("freq_arena"), sym("an arena, not a song"), sym("a"), sym("b"), sym("c"), sym("d")]))
+    records.append(("tree", 16, 31, [sym("SHORT"), sym("five fields only"), sym("a"), sym("b"), sym("c")]))
+    unlocks = [sym("campaign")]
+    for i, sg in enumerate(SONGS):
+        if sg["unlock_method"]:
+            unlocks.append(("tree", 16, 60 + i, [sym(sg["unlock_method"]), ("int", 0, sg["unlock_count"]),
+                                                 sym("kUnlockArena"), sym(sg["id"])]))
+    amp_config = ("tree", 16, 1, [("tree", 16, 2, records), ("tree", 16, 50, unlocks), ("int", 6, 12345)])
+
+    arenas = {}
+    for sg in SONGS:
+        if sg["path"]:
+            arenas.setdefault(sg["arena"], []).append(sg)
+    groups = []
+    for gi, (arena, members) in enumerate(sorted(arenas.items())):
+        kids = [sym(arena)]
+        for mi, sg in enumerate(members):
+            kids.append(("tree", 16, 100 + 10 * gi + mi, [sym(sg["id"]), sym(sg["path"], 33),
+                                                         ("tree", 16, 200 + 10 * gi + mi, [sym("type"), sym(sg["type"])])]))
+        groups.append(("tree", 16, 90 + gi, kids))
+    amp_songs_config = ("tree", 16, 1, groups)
+    return do.serialise([amp_config]), do.serialise([amp_songs_config])
+
+
+def fixture_file_bytes(f) -> bytes:
+    """Contents of one input file of the reference-generated fixtures (tests/golden/ark/manifest.json): the
+    two DTA configs are real DTB (song_config_blobs), everything else is synth.payload(seed, size)."""
+    if f.get("content") == "amp_config":
+        return song_config_blobs()[0]
+    if f.get("content") == "amp_songs_config":
+        return song_config_blobs()[1]
+    return synth.payload(f["seed"], f["size"]).tobytes()

@@ -24,7 +24,8 @@ def test_reference_arm_line():
     d = run_bench("--impl", "reference", "--steps", "1", "--warmup", "0")
     assert COMMON <= set(d) and d["impl"] == "reference"
     assert d["unit"] == "GB/s" and d["value"] > 0 and d["higher_is_better"] is True
-    assert d["config"]["workload"] == "cfg2" and d["dtype"] == "u8"
+    assert d["config"]["workload"] == "cfg3" and d["dtype"] == "u8" and d["scaling"] == "strong"
+    assert d["config"]["payload_bytes"] == 16 << 30 and d["config"]["entries"] == 32
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -33,18 +34,27 @@ def test_reference_arm_line():
 
 @pytest.mark.gpu
 def test_gpu_arm_line():
+    """The headline line: BASELINE configs[2] (16 GiB multi-part set), parity checked in the run."""
     d = run_bench("--steps", "5", "--warmup", "3")
-    assert COMMON | {"roofline", "clocks"} <= set(d) and "impl" not in d
-    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["scaling"] == "weak"
-    assert d["config"]["workload"] == "cfg2" and d["dtype"] == "u8" and d["data"] == "synthetic"
+    assert COMMON | {"roofline", "clocks", "parity_bytes_checked", "extra"} <= set(d) and "impl" not in d
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["scaling"] == "strong"
+    assert d["config"]["workload"] == "cfg3" and d["dtype"] == "u8" and d["data"].startswith("synthetic")
+    assert d["config"]["payload_bytes"] == 16 << 30
+    assert d["parity_bytes_checked"] >= 64 << 20
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert r["algorithmic_bytes_per_launch"] == 2 * d["config"]["payload_bytes_per_gpu"]
-    assert 0.3 < r["frac"] < 1.2
+    assert r["algorithmic_bytes_per_launch"] == 2 * d["config"]["payload_bytes"]
+    assert 0.3 < r["frac"] < 1.25
+    s = r["sustained"]
+    assert s["seconds"] >= 3.0 and 0.3 < s["frac"] < 1.25 and s["clocks"]["samples"] > 10
     assert d["gpu_launches"] == 2 * d["steps"]          # HDR Cycle + one batched launch per step
     e = d["e2e"]
-    assert e["h2d_bytes_per_step"] > d["config"]["payload_bytes_per_gpu"] and e["d2h_bytes_per_step"] > 0
-    assert 0 < e["value"] < d["value"]
+    assert e["h2d_bytes_per_step"] > d["config"]["payload_bytes"] and e["d2h_bytes_per_step"] > 0
+    assert 0 < e["value"] < d["value"] and e["parity_bytes_checked"] > 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] in ("reference", "port") and cb["gpu_bytes_checked_against_it"] > 0
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0
     assert d["clocks"]["sm_max_mhz"] and isinstance(d["clocks"]["reasons"], list)
+    for w, entries in (("cfg2", 10_000), ("cfg4", 1_000_000)):
+        x = d["extra"][w]
+        assert x["config"]["workload"] == w and x["config"]["entries"] == entries
+        assert x["parity_bytes_checked"] > 0 and 0.3 < x["roofline"]["frac"] < 1.25

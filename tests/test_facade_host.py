@@ -159,15 +159,25 @@ def test_pack_filters_unknown_files_and_songs(cli, tmp_path):
     hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), n_files=50, n_parts=2, seed=13)
     run(cli, tmp_path, "-unpack", "unpacked")
     (tmp_path / "unpacked" / "ps4" / "brand_new.bin").write_bytes(b"new file")
+    # like the reference (Modulate.cpp:410-432), -pack without -packall takes its song list from the two DTA
+    # configs of the input tree and fails loudly without them (it used to drop every song silently)
+    assert "Failed to open file" in run(cli, tmp_path, "-pack", "unpacked", "r0", expect=1)
+    cfg, songs_cfg = arkfixture.song_config_blobs()
+    (tmp_path / "unpacked" / "ps4" / "config").mkdir(parents=True, exist_ok=True)
+    (tmp_path / "unpacked" / "ps4" / "config" / "amp_config.dta_dta_ps4").write_bytes(cfg)
+    (tmp_path / "unpacked" / "ps4" / "config" / "amp_songs_config.dta_dta_ps4").write_bytes(songs_cfg)
     run(cli, tmp_path, "-pack", "unpacked", "r1")                       # default: ignore new + /songs/ filter
     new, _ = arkfixture.read_header(str(tmp_path / "r1" / "main_ps4.hdr"))
     names = {e.name for e in new.entries}
     assert "ps4/brand_new.bin" not in names
-    assert not any("/songs/custom1/" in n for n in names)
+    # CUSTOM1 is in the configs, so its folder is kept (an unconfigured folder being dropped is pinned by the
+    # reference-generated fixtures: tests/test_ref_fixtures.py, /songs/Custom_Two/)
+    assert {n for n in names if "/songs/custom1/" in n} == {e.name for e in hdr.entries if "/songs/custom1/" in e.name}
     assert any("/songs/credits/" in n for n in names) or not any("/songs/credits/" in e.name for e in hdr.entries)
     run(cli, tmp_path, "-packall", "-pack_add", "unpacked", "r2")      # everything
     new2, _ = arkfixture.read_header(str(tmp_path / "r2" / "main_ps4.hdr"))
-    assert {e.name for e in new2.entries} == {e.name for e in hdr.entries} | {"ps4/brand_new.bin"}
+    assert {e.name for e in new2.entries} == {e.name for e in hdr.entries} | {
+        "ps4/brand_new.bin", "ps4/config/amp_config.dta_dta_ps4", "ps4/config/amp_songs_config.dta_dta_ps4"}
 
 
 def test_header_codec_roundtrip_python_side():

@@ -236,3 +236,28 @@ def test_contexts_survive_device_switch(mb):
     for b in (d0, d1):
         b.free()
     plan0.close()
+
+
+def test_general_kernel_on_coaligned_tiles(mb, monkeypatch):
+    """The launch picks the co-aligned kernel when every entry agrees with the base pointers mod 16 and
+    the general (shared-memory staged, funnel-shifting) kernel otherwise; both must give the same bytes.
+    MOD_FORCE_GENERAL sends co-aligned work through the general kernel."""
+    n = 300
+    sizes = synth.entry_sizes_loguniform(n, 6 << 20, lo=1, hi=1 << 17, seed=13)
+    off = synth.packed_offsets(sizes) + 3
+    descs = mb.make_descs(off, off, sizes, synth.entry_keys(n, seed=5))
+    src_np = synth.payload(8, int((off + sizes).max()) + 5)
+    want = oracle.cycle_batch(descs, src_np, src_np.copy())
+    for force in (False, True):
+        if force:
+            monkeypatch.setenv("MOD_FORCE_GENERAL", "1")
+        buf = DeviceBuffer.from_numpy(src_np)
+        plan = mb.Plan(descs, src_np.size, src_np.size)
+        plan.run(buf.ptr, buf.ptr)
+        sync()
+        assert (buf.download() == want).all(), force
+        mb.cycle_device(buf.ptr, buf.ptr, src_np.size, 77)  # contiguous kernel, same two flavours
+        sync()
+        assert (buf.download() == oracle.cycle(want, 77)).all(), force
+        plan.close()
+        buf.free()

@@ -27,6 +27,7 @@ import oracle
 import synth
 from oracle import ark_oracle as ao
 from oracle import dta_oracle as do
+from arkfixture import fixture_file_bytes
 from test_facade_host import cli, run  # noqa: F401  (fixture + helper)
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -34,6 +35,7 @@ with open(os.path.join(GOLD, "ark", "manifest.json")) as _f:
     MANIFEST = json.load(_f)
 with open(os.path.join(GOLD, "dtb", "index.json")) as _f:
     DTB_INDEX = json.load(_f)
+SONGS = MANIFEST.pop("songs")
 CASES = sorted(MANIFEST)
 
 
@@ -107,11 +109,12 @@ def test_fixtures_cover_the_edge_cases():
         buckets = [ao.file_hash(f["name"], n) for f in files]
         assert len(set(buckets)) < n  # colliding name-hash buckets -> flags1 chains
         assert any(f["flags1"] != -1 for f in files)
-    # -pack with the /songs/ filter dropped the songs outside the built-in list and the new files
+    # -pack: the song list came from the DTA configs (CUSTOM1 is configured, Custom_Two is not), the
+    # built-in songs are always kept, new files are ignored
     for plat in ("ps3", "ps4"):
         names = {f["name"] for f in MANIFEST[f"{plat}_pack"]["loaded_files"]}
-        assert not any("/songs/custom1/" in n or "/songs/Custom_Two/" in n or "zz_new_file" in n for n in names)
-        assert any("/songs/credits/" in n for n in names)
+        assert not any("/songs/Custom_Two/" in n or "zz_new_file" in n for n in names)
+        assert any("/songs/credits/" in n for n in names) and any("/songs/Custom1/" in n for n in names)
 
 
 # ---- the product's host-side C++ against the reference's output ------------------------------------------
@@ -124,7 +127,7 @@ def stage_case(tmp_path, case):
     for f in info["input"]:
         path = tmp_path / "in" / f["name"]
         path.parent.mkdir(parents=True, exist_ok=True)
-        path.write_bytes(synth.payload(f["seed"], f["size"]).tobytes())
+        path.write_bytes(fixture_file_bytes(f))
     args = ([] if plat == "ps4" else ["-ps3"]) + (["-packall"] if info["pack_all"] else [])
     args += ["-pack" if info["ignore_new"] else "-pack_add", "in", "out"]
     return info, plat, args
@@ -155,7 +158,7 @@ def test_cpp_unpack_of_reference_written_archive(cli, tmp_path, case):
     image = bytearray(sum(p["size"] for p in info["loaded_parts"]))
     for f in info["loaded_files"]:
         src = by_name[f["name"]]
-        image[f["offset"]:f["offset"] + f["size"]] = synth.payload(src["seed"], src["size"]).tobytes()
+        image[f["offset"]:f["offset"] + f["size"]] = fixture_file_bytes(src)
     pos = 0
     for part, digest in zip(info["loaded_parts"], info["part_sha256"]):
         blob = bytes(image[pos:pos + part["size"]])
@@ -165,6 +168,24 @@ def test_cpp_unpack_of_reference_written_archive(cli, tmp_path, case):
     run(cli, tmp_path, *([] if plat == "ps4" else ["-ps3"]), "-unpack", "ext")
     for name, digest in info["extracted_sha256"].items():
         assert sha((tmp_path / "ext" / name).read_bytes()) == digest, name
+
+
+def test_cpp_song_list_matches_reference_getsongs(cli, tmp_path):
+    """GetSongs + GetSongData (CDtaFile.cpp:102-181, :248-294) through the CLI's -listsongs, against the
+    list the reference derived from the same two configs."""
+    import arkfixture
+    cfg, songs_cfg = arkfixture.song_config_blobs()
+    d = tmp_path / "in" / "ps4" / "config"
+    d.mkdir(parents=True)
+    (d / "amp_config.dta_dta_ps4").write_bytes(cfg)
+    (d / "amp_songs_config.dta_dta_ps4").write_bytes(songs_cfg)
+    out = run(cli, tmp_path, "-listsongs", "in")
+    assert len(SONGS) == 3 and SONGS[0]["path"] == "../songs/custom1/custom1.moggsong"  # lower-cased by GetSongData
+    for i, sg in enumerate(SONGS):
+        want = (f"Song {i + 1}\t  {sg['id']} - {sg['name']} - {sg['type']}\n\t  {sg['path']}\n\t  Unlocked by "
+                f"{sg['unlock_method']} {sg['unlock_count']}\n\t  Arena: {sg['arena']}\n")
+        assert want in out, (want, out)
+    assert f"Song {len(SONGS) + 1}" not in out
 
 
 # ---- DTB ----------------------------------------------------------------------------------------------------
