@@ -23,7 +23,8 @@ one.  `parity_bytes_checked` is the sum over ranks; any mismatch ends the run wi
 
 At N == 1 the line also carries `extra.cfg2` (1 GiB / 10 000 entries, misaligned gather; BASELINE
 configs[1]) and `extra.cfg4` (1 000 000 entries of 1..64 KiB, one launch; configs[3]), each with its
-own roofline and parity count, `roofline.sustained` (>= 3 s of back-to-back launches with NVML clock /
+own roofline and parity count, `extra.cfg5` (configs[4]: unpack -> DTA patch -> repack of a 1 GiB
+archive through the CArk facade on a RAM-backed file system, every output byte checked), `roofline.sustained` (>= 3 s of back-to-back launches with NVML clock /
 power samples) next to the burst figure, and `cpu_baseline` (the unmodified reference cipher on the
 host cores, bounded sample).  The CPU numbers are a baseline, not the target -- the target is
 roofline.frac.
@@ -262,6 +263,8 @@ def run_reference_arm(args) -> None:
     import modulate_b200 as mb  # host-only use: make_descs (no GPU work on this arm)
     import oracle
     kind = "reference" if oracle.have_ref() else "port"
+    if args.workload == "cfg5":  # the repack set is the cfg2 archive: the CPU arm ciphers its entries
+        args.workload = "cfg2"
     descs = global_descs(mb, args.workload)
     sample = cpu_sample(descs, args.workload)
     cores = min(os.cpu_count() or 1, len(sample["parts"]))  # one reference Cycle() per part: at most that many threads
@@ -623,8 +626,107 @@ def inprocess_e2e(c: Ctx, args) -> dict:
             "api": "mod_cycle_batch_sharded on one pinned host buffer, ONE process driving all devices"}
 
 
+def measure_cfg5(c: Ctx, total: int = GIB, n_files: int = 10_000) -> dict:
+    """BASELINE configs[4], end to end through the archive-level facade (include/modulate_ark.h) on a
+    RAM-backed file system: a 1 GiB / 10 000-entry archive whose bodies are ciphered per entry is
+    (1) unpacked -- CArk::Load + ExtractFiles: part files -> pinned slots -> GPU gather + decipher ->
+    files, (2) one binary DTA entry is patched on the host (CDtaFile), (3) repacked --
+    ConstructFromDirectory + BuildArk + SaveArk: files -> pinned slots -> GPU encipher -> part files,
+    header re-serialised and re-enciphered.  Afterwards (untimed) every output byte is compared with
+    what the CPU oracle says the repacked HDR and ARK must be."""
+    import shutil
+    import tempfile
+
+    import arkfixture
+    import oracle
+    from oracle import ark_oracle as ao
+    from oracle import dta_oracle as do
+    from test_dta_codec import song_config_tree
+
+    mb = c.mb
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    root = tempfile.mkdtemp(prefix="mod_cfg5_", dir=base)
+    key = 0x0BADF00D
+    try:
+        sizes = [int(x) for x in synth.entry_sizes_loguniform(n_files, total, lo=1 << 10, hi=1 << 20, seed=7)]
+        tree = song_config_tree()
+        dtb = do.serialise([tree])
+        victim = 1234 % n_files
+        sizes[0] += sizes[victim] - len(dtb)  # keep the total: the DTB entry has its own size
+        sizes[victim] = len(dtb)
+        hdr, payloads, _ = arkfixture.write_archive(root, n_files=n_files, n_parts=2, seed=5, body_key=key, sizes=sizes,
+                                                    contents={victim: dtb})
+        victim_name = hdr.entries[victim].name
+        hdr_path = os.path.join(root, "main_ps4.hdr")
+        out_dir, re_dir = os.path.join(root, "out"), os.path.join(root, "re")
+        os.makedirs(re_dir)
+        mb.ark_unpack(hdr_path, root, os.path.join(root, "warm"), key)  # warm-up: CUDA context, page cache, pinned pools
+        shutil.rmtree(os.path.join(root, "warm"))
+
+        t0 = time.perf_counter()
+        mb.ark_unpack(hdr_path, root, out_dir, key)
+        t1 = time.perf_counter()
+        mb.dta_set_int(os.path.join(out_dir, victim_name), "bpm", 174)
+        t2 = time.perf_counter()
+        mb.ark_pack(hdr_path, out_dir, re_dir, "main_ps4.hdr", ps4=True, pack_all=True, ignore_new_files=False, body_key=key)
+        t3 = time.perf_counter()
+
+        # -- what the repacked archive must be, from the oracle: walk order, BuildArk offsets / parts, bodies
+        #    re-enciphered per entry, header serialised in PS4 order and enciphered
+        kids, i = do.find_node(tree, b"bpm")
+        kids[i + 1] = ("int", 0, 174)
+        by_name = {e.name: p for e, p in zip(hdr.entries, payloads)}
+        by_name[victim_name] = do.serialise([tree])
+        walk = arkfixture.reconstruct_walk(sorted(by_name))
+        wsizes = [len(by_name[n]) for n in walk]
+        offsets, parts = ao.build_ark(wsizes, ao.plan_part_sizes(sum(wsizes), len(hdr.parts)))
+        image = np.frombuffer(b"".join(by_name[n] for n in walk), dtype=np.uint8).copy()
+        packed_off = synth.packed_offsets(np.array(wsizes, dtype=np.int64))
+        arkfixture.cipher_entries(image, packed_off, wsizes, key)
+        model = ao.Header(ps4=True, parts=[(p, s) for (p, _), s in zip(hdr.parts, parts)],
+                          entries=[ao.Entry(name=n, offset=o, size=s) for n, o, s in zip(walk, offsets, wsizes)])
+        plain = ao.serialise_header(model)
+        want_hdr = plain[:4] + oracle.cycle(np.frombuffer(plain[4:], dtype=np.uint8), ao.KEY_PS4).tobytes()
+        got_hdr = open(os.path.join(re_dir, "main_ps4.hdr"), "rb").read()
+        if got_hdr != want_hdr:
+            raise SystemExit("PARITY FAILURE (cfg5): repacked HDR differs from the oracle")
+        checked = len(got_hdr)
+        pos = 0
+        for (pth, _), psize in zip(hdr.parts, parts):
+            got = np.fromfile(os.path.join(re_dir, pth), dtype=np.uint8)
+            if got.size != psize or not np.array_equal(got, image[pos:pos + psize]):
+                raise SystemExit(f"PARITY FAILURE (cfg5): repacked part {pth} differs from the oracle")
+            pos += psize
+            checked += psize
+        for e, p in list(zip(hdr.entries, payloads))[::97]:  # and a sample of the extracted files
+            want = by_name[e.name] if e.name == victim_name else p
+            if open(os.path.join(out_dir, e.name), "rb").read() != want:
+                raise SystemExit(f"PARITY FAILURE (cfg5): extracted {e.name} differs")
+            checked += len(want)
+        payload = sum(wsizes)
+        return {"value": 2 * payload / (t3 - t0) / 1e9, "unit": "GB/s",
+                "what": "payload bytes extracted + payload bytes repacked, per second of wall clock (unpack + DTA patch + pack)",
+                "unpack_s": t1 - t0, "dta_patch_s": t2 - t1, "pack_s": t3 - t2,
+                "unpack_gbs": payload / (t1 - t0) / 1e9, "pack_gbs": payload / (t3 - t2) / 1e9,
+                "entries": n_files, "payload_bytes": payload, "parity_bytes_checked": checked,
+                "file_system": base, "host_threads": os.cpu_count(),
+                "api": "mod_ark_unpack + mod_dta_set_int + mod_ark_pack (CArk / CDtaFile facade) on files"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def run_gpu_arm(args) -> None:
     c = Ctx()
+    if args.workload == "cfg5":
+        if c.rank == 0:
+            r = measure_cfg5(c)
+            print(json.dumps({"metric": METRIC, "value": r["value"], "unit": "GB/s", "n_gpus": 1, "steps": 1, "warmup": 1,
+                              "ms_per_step": 1e3 * (r["unpack_s"] + r["dta_patch_s"] + r["pack_s"]), "higher_is_better": True,
+                              "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                              "config": {"workload": "cfg5", "entries": r["entries"], "payload_bytes": r["payload_bytes"]},
+                              "e2e": r, "parity_bytes_checked": r["parity_bytes_checked"]}), flush=True)
+        c.finish()
+        return
     if c.world != args.gpus and not (c.world == 1 and args.gpus == 1):
         if c.world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
@@ -649,6 +751,14 @@ def run_gpu_arm(args) -> None:
                     r = measure_workload(c, sub_args, w, full=False)
                     extra[w] = {k: r[k] for k in ("value", "ms_per_step", "kernel_ms", "parity_bytes_checked",
                                                   "roofline", "config", "gpu_launches")}
+            if c.rank == 0:
+                os.sched_setaffinity(0, c.all_cpus)  # the file pipelines use every host core
+                try:
+                    extra["cfg5"] = measure_cfg5(c)
+                except SystemExit:
+                    raise
+                except Exception as exc:  # reported, never fatal for the headline line
+                    extra["cfg5"] = {"error": repr(exc)[:300]}
     if c.rank != 0:
         c.finish()
         return
@@ -693,7 +803,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--kernel-only", action="store_true",
                     help="profiling aid: device-resident legs only (no sustained run, e2e, extras or CPU baseline)")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra.cfg2 / extra.cfg4 / in-process blocks")

@@ -68,6 +68,10 @@ int mod_device_count(void);
 /* Bind the calling process to `device` (-1 = keep the current device), create the internal
  * streams and upload the jump tables.  Idempotent.  Called implicitly by the compute entry points. */
 int mod_init(int device);
+/* The CUDA device the calling thread is bound to, or a negative MOD_ERR_*. */
+int mod_current_device(void);
+/* 1 if `p` points into device (or managed) memory, 0 if it is a host pointer. */
+int mod_is_device_pointer(const void* p);
 void mod_shutdown(void);
 const char* mod_last_error(void);
 /* Kernels this library has launched in this process (all streams): bench.py's gpu_launches. */

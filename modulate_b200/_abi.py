@@ -29,6 +29,8 @@ SIGNATURES = {
     "mod_abi_version": (ctypes.c_int, []),
     "mod_device_count": (ctypes.c_int, []),
     "mod_init": (ctypes.c_int, [ctypes.c_int]),
+    "mod_current_device": (ctypes.c_int, []),
+    "mod_is_device_pointer": (ctypes.c_int, [ctypes.c_void_p]),
     "mod_shutdown": (None, []),
     "mod_last_error": (ctypes.c_char_p, []),
     "mod_launch_count": (ctypes.c_uint64, []),
@@ -61,6 +63,11 @@ SIGNATURES = {
                                        ctypes.c_void_p, ctypes.c_uint64]),
     "mod_cycle_batch_sharded": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
                                                ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]),
+    # include/modulate_ark.h: C binding of the archive-level facade
+    "mod_ark_unpack": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32]),
+    "mod_ark_pack": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_int32]),
+    "mod_dta_set_int": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int32]),
     "mod_shard_range": (ctypes.c_int, [ctypes.c_uint64, ctypes.c_int, ctypes.c_int,
                                        ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "mod_shard_descs": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int,

@@ -214,3 +214,40 @@ def shard_descs(descs: np.ndarray, rank: int, world: int) -> np.ndarray:
     if n:
         _abi.check(L.mod_shard_descs(ptr, len(d), rank, world, out.ctypes.data, n))
     return out
+
+
+# ---- archive-level facade (include/modulate_ark.h): the reference's Unpack / Pack command bodies ----------
+
+class ArkError(RuntimeError):
+    """Carries the reference's eError code (Error.h:5-20)."""
+
+    def __init__(self, code: int, what: str):
+        super().__init__(f"{what} failed with eError {code}")
+        self.code = code
+
+
+def _slash(path: str) -> bytes:
+    return (path if path.endswith("/") else path + "/").encode()
+
+
+def ark_unpack(header_path: str, part_dir: str, target_dir: str, body_key: int = 0) -> None:
+    """``CArk::Load`` + ``CArk::ExtractFiles`` (reference Modulate.cpp:291-317)."""
+    rc = _abi.load().mod_ark_unpack(header_path.encode(), _slash(part_dir) if part_dir else b"", _slash(target_dir),
+                                    _i32(body_key))
+    if rc:
+        raise ArkError(rc, "mod_ark_unpack")
+
+
+def ark_pack(reference_header_path: str, input_dir: str, output_dir: str, header_name: str, *, ps4: bool = True,
+             pack_all: bool = False, ignore_new_files: bool = True, body_key: int = 0) -> None:
+    """The reference's Pack (Modulate.cpp:380-450): ``ConstructFromDirectory`` + ``BuildArk`` + ``SaveArk``."""
+    rc = _abi.load().mod_ark_pack(reference_header_path.encode(), _slash(input_dir), _slash(output_dir),
+                                  header_name.encode(), int(ps4), int(pack_all), int(ignore_new_files), _i32(body_key))
+    if rc:
+        raise ArkError(rc, "mod_ark_pack")
+
+
+def dta_set_int(dta_path: str, key: str, value: int) -> None:
+    rc = _abi.load().mod_dta_set_int(dta_path.encode(), key.encode(), int(value))
+    if rc:
+        raise ArkError(rc, "mod_dta_set_int")

@@ -1,8 +1,10 @@
 #include "CArk.h"
 
 #include <dirent.h>
+#include <fcntl.h>
 #include <sys/stat.h>
 #include <sys/types.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -11,8 +13,11 @@
 #include <condition_variable>
 #include <cstdlib>
 #include <deque>
+#include <functional>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
+#include <unordered_set>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -133,6 +138,235 @@ void ListFiles(const std::string& lRoot, const std::string& lRelative, std::vect
         ListFiles(lRoot, lRelative + lName + "/", laOut);
 }
 
+// mkdir -p with a per-thread memo of directories already known to exist (thousands of entries share
+// a handful of folders; the reference re-runs _mkdir + stat for every component of every file,
+// CArk.cpp:463-483).
+bool MakeParentDirectoriesCached(const std::string& lFilePath, std::unordered_set<std::string>& lKnown)
+{
+    const size_t liLast = lFilePath.rfind('/');
+    if (liLast == std::string::npos || liLast == 0)
+        return true;
+    if (lKnown.count(lFilePath.substr(0, liLast)))
+        return true;
+    if (!MakeParentDirectories(lFilePath))
+        return false;
+    lKnown.insert(lFilePath.substr(0, liLast));
+    return true;
+}
+
+// A few worker threads draining a queue of closures: the reader and writer stages of the pipelines.
+class TaskPool
+{
+public:
+    explicit TaskPool(int liThreads)
+    {
+        for (int ii = 0; ii < liThreads; ++ii)
+            maThreads.emplace_back([this]() { Loop(); });
+    }
+    ~TaskPool() { Finish(); }
+    void Push(std::function<void()> lTask)
+    {
+        {
+            std::lock_guard<std::mutex> lLock(mMutex);
+            maTasks.push_back(std::move(lTask));
+        }
+        mSignal.notify_one();
+    }
+    void Finish()  // run what is queued, then stop
+    {
+        {
+            std::lock_guard<std::mutex> lLock(mMutex);
+            mbClosed = true;
+        }
+        mSignal.notify_all();
+        for (std::thread& lThread : maThreads)
+            if (lThread.joinable())
+                lThread.join();
+    }
+
+private:
+    void Loop()
+    {
+        for (;;) {
+            std::function<void()> lTask;
+            {
+                std::unique_lock<std::mutex> lLock(mMutex);
+                mSignal.wait(lLock, [this]() { return !maTasks.empty() || mbClosed; });
+                if (maTasks.empty())
+                    return;
+                lTask = std::move(maTasks.front());
+                maTasks.pop_front();
+            }
+            lTask();
+        }
+    }
+    std::mutex mMutex;
+    std::condition_variable mSignal;
+    std::deque<std::function<void()>> maTasks;
+    std::vector<std::thread> maThreads;
+    bool mbClosed = false;
+};
+
+int HostThreads()
+{
+    const unsigned int luCores = std::thread::hardware_concurrency();
+    return luCores ? (int)luCores : 4;
+}
+
+// GPUs the facade spreads an archive over: every visible device (MOD_DEVICES = bit mask restricts
+// them) once the archive is large enough to be worth it, else only the calling thread's device.
+std::vector<int> FacadeDevices(uint64_t luBytes)
+{
+    std::vector<int> laDevices;
+    const int liCurrent = std::max(0, mod_current_device());
+    const int liCount = mod_device_count();
+    const char* lpMask = std::getenv("MOD_DEVICES");
+    const uint64_t luMask = lpMask && *lpMask ? std::strtoull(lpMask, nullptr, 0) : 0;
+    const uint64_t kuMultiGpuThreshold = 256ull << 20;
+    if (liCount > 1 && luBytes >= kuMultiGpuThreshold)
+        for (int ii = 0; ii < liCount && ii < 64; ++ii)
+            if (luMask == 0 || ((luMask >> ii) & 1ull))
+                laDevices.push_back(ii);
+    if (laDevices.empty())
+        laDevices.push_back(liCurrent);
+    return laDevices;
+}
+
+// One stage buffer set of the streaming pipelines: pinned host memory either side of the GPU, the
+// two HBM windows the batched kernel works on, and the stream that orders upload -> kernel -> download.
+struct Slot {
+    enum eState { eFree, eFilling, eFilled, eDraining };
+    int miDevice = 0;
+    unsigned char* mpHostIn = nullptr;   // what the readers fill (image range / input files)
+    unsigned char* mpHostOut = nullptr;  // what the writers drain (extracted files / ciphered image range)
+    void* mpDevIn = nullptr;
+    void* mpDevOut = nullptr;
+    void* mpStream = nullptr;
+    eState meState = eFree;
+    int miFillLeft = 0;
+    int miDrainLeft = 0;
+    bool mbUsedGpu = false;
+};
+
+struct SlotRing {
+    std::vector<Slot> maSlots;
+    std::mutex mMutex;
+    std::condition_variable mSignal;
+    std::atomic<int> miError{(int)eError_NoError};
+
+    void Fail(eError leWhat)
+    {
+        int liExpected = (int)eError_NoError;
+        miError.compare_exchange_strong(liExpected, (int)leWhat);
+        mSignal.notify_all();
+    }
+    bool Failed() const { return miError.load() != (int)eError_NoError; }
+    void Set(Slot& lSlot, Slot::eState leState)
+    {
+        {
+            std::lock_guard<std::mutex> lLock(mMutex);
+            lSlot.meState = leState;
+        }
+        mSignal.notify_all();
+    }
+    // one unit of fill / drain work done; the last one flips the slot's state
+    void FillDone(Slot& lSlot)
+    {
+        bool lbLast = false;
+        {
+            std::lock_guard<std::mutex> lLock(mMutex);
+            lbLast = --lSlot.miFillLeft == 0;
+            if (lbLast)
+                lSlot.meState = Slot::eFilled;
+        }
+        if (lbLast)
+            mSignal.notify_all();
+    }
+    void DrainDone(Slot& lSlot)
+    {
+        bool lbLast = false;
+        {
+            std::lock_guard<std::mutex> lLock(mMutex);
+            lbLast = --lSlot.miDrainLeft == 0;
+            if (lbLast)
+                lSlot.meState = Slot::eFree;
+        }
+        if (lbLast)
+            mSignal.notify_all();
+    }
+    // Allocate liPerDevice slots on each device: pinned buffers of luInBytes / luOutBytes, HBM windows
+    // of the same sizes (+ slack for the 16-byte phase), one stream each.
+    bool Allocate(const std::vector<int>& laDevices, int liPerDevice, size_t liGroups, uint64_t luInBytes, uint64_t luOutBytes,
+                  bool lbNeedGpu)
+    {
+        const size_t liWanted = std::min(liGroups, (size_t)liPerDevice * laDevices.size());
+        maSlots.resize(std::max<size_t>(1, liWanted));
+        for (size_t ii = 0; ii < maSlots.size(); ++ii) {
+            Slot& lSlot = maSlots[ii];
+            lSlot.miDevice = laDevices[ii % laDevices.size()];
+            lSlot.mpHostIn = (unsigned char*)mod_host_alloc(luInBytes + 32);
+            lSlot.mpHostOut = (unsigned char*)mod_host_alloc(luOutBytes + 32);
+            if (!lSlot.mpHostIn || !lSlot.mpHostOut)
+                return false;
+            if (lbNeedGpu) {
+                if (mod_init(lSlot.miDevice) != MOD_OK)
+                    return false;
+                lSlot.mpDevIn = mod_device_alloc(luInBytes + 32);
+                lSlot.mpDevOut = mod_device_alloc(luOutBytes + 32);
+                lSlot.mpStream = mod_stream_create();
+                if (!lSlot.mpDevIn || !lSlot.mpDevOut || !lSlot.mpStream)
+                    return false;
+            }
+        }
+        return true;
+    }
+    void Release()
+    {
+        for (Slot& lSlot : maSlots) {
+            if (lSlot.mpStream) {
+                mod_stream_sync(lSlot.mpStream);
+                mod_stream_destroy(lSlot.mpStream);
+            }
+            mod_device_free(lSlot.mpDevIn);
+            mod_device_free(lSlot.mpDevOut);
+            mod_host_free(lSlot.mpHostIn);
+            mod_host_free(lSlot.mpHostOut);
+        }
+        maSlots.clear();
+    }
+};
+
+// pread / pwrite the whole range (short transfers are retried; a short FILE reads as zeros).
+bool ReadFully(int liFd, unsigned char* lpDst, uint64_t luSize, uint64_t luOffset)
+{
+    while (luSize) {
+        const ssize_t liGot = pread(liFd, lpDst, (size_t)std::min<uint64_t>(luSize, 1u << 30), (off_t)luOffset);
+        if (liGot < 0)
+            return false;
+        if (liGot == 0) {
+            std::memset(lpDst, 0, (size_t)luSize);
+            return true;
+        }
+        lpDst += liGot;
+        luOffset += (uint64_t)liGot;
+        luSize -= (uint64_t)liGot;
+    }
+    return true;
+}
+
+bool WriteFully(int liFd, const unsigned char* lpSrc, uint64_t luSize, uint64_t luOffset)
+{
+    while (luSize) {
+        const ssize_t liPut = pwrite(liFd, lpSrc, (size_t)std::min<uint64_t>(luSize, 1u << 30), (off_t)luOffset);
+        if (liPut <= 0)
+            return false;
+        lpSrc += liPut;
+        luOffset += (uint64_t)liPut;
+        luSize -= (uint64_t)liPut;
+    }
+    return true;
+}
+
 }  // namespace
 
 CArk::CArk() {}
@@ -209,11 +443,11 @@ eError CArk::Load(const char* lpHeaderFilename)
 // Read the parts back to back into the pinned image (reference CArk.cpp:741-755).
 eError CArk::ReadParts()
 {
-    std::vector<FILE*> lFiles(mHeader.maParts.size(), nullptr);
-    const bool lbOk = ReadImageRange(lFiles, 0, muArkDataSize, mpArkData);
-    for (FILE* lpFile : lFiles)
-        if (lpFile)
-            std::fclose(lpFile);
+    std::vector<int> laFds;
+    const bool lbOk = ReadImageRange(laFds, 0, muArkDataSize, mpArkData);
+    for (int liFd : laFds)
+        if (liFd >= 0)
+            close(liFd);
     return lbOk ? eError_NoError : eError_FailedToOpenFile;
 }
 
@@ -232,6 +466,8 @@ eError CArk::AllocateArkData()
     return eError_NoError;
 }
 
+// The reference's whole-image load (CArk.cpp:723-758), kept for callers that want the flat image;
+// ExtractFiles does not need it any more (it streams ranges through a slot ring).
 eError CArk::LoadArkData()
 {
     eError leError = AllocateArkData();
@@ -241,26 +477,34 @@ eError CArk::LoadArkData()
     return eError_NoError;
 }
 
-// Copy bytes [luOffset, luOffset + luSize) of the concatenated part files into lpDst, opening each
-// part on demand (lFiles caches the handles).  Bytes a short part file does not have read as zero.
-bool CArk::ReadImageRange(std::vector<FILE*>& lFiles, uint64_t luOffset, uint64_t luSize, unsigned char* lpDst) const
+// Copy bytes [luOffset, luOffset + luSize) of the concatenated part files into lpDst with pread (safe
+// from several threads at once), opening each part on first use (laFds caches the descriptors; it
+// must be sized and guarded by the caller when shared).  Bytes a short part file lacks read as zero.
+bool CArk::ReadImageRange(std::vector<int>& laFds, uint64_t luOffset, uint64_t luSize, unsigned char* lpDst) const
 {
+    static std::mutex lOpenMutex;
+    {
+        std::lock_guard<std::mutex> lLock(lOpenMutex);
+        if (laFds.size() < mHeader.maParts.size())
+            laFds.resize(mHeader.maParts.size(), -1);
+    }
     uint64_t luPartStart = 0;
     for (size_t ii = 0; ii < mHeader.maParts.size() && luSize; ++ii) {
         const uint64_t luPartSize = mHeader.maParts[ii].muSize;
         const uint64_t luPartEnd = luPartStart + luPartSize;
         if (luOffset < luPartEnd) {
-            if (!lFiles[ii]) {
-                lFiles[ii] = std::fopen((mPartDirectory + mHeader.maParts[ii].mPath).c_str(), "rb");
-                if (!lFiles[ii])
-                    return false;
+            int liFd;
+            {
+                std::lock_guard<std::mutex> lLock(lOpenMutex);
+                if (laFds[ii] < 0)
+                    laFds[ii] = open((mPartDirectory + mHeader.maParts[ii].mPath).c_str(), O_RDONLY);
+                liFd = laFds[ii];
             }
-            const uint64_t luTake = std::min(luSize, luPartEnd - luOffset);
-            if (fseeko(lFiles[ii], (off_t)(luOffset - luPartStart), SEEK_SET) != 0)
+            if (liFd < 0)
                 return false;
-            const size_t liRead = std::fread(lpDst, 1, (size_t)luTake, lFiles[ii]);
-            if (liRead != luTake)
-                std::memset(lpDst + liRead, 0, (size_t)luTake - liRead);
+            const uint64_t luTake = std::min(luSize, luPartEnd - luOffset);
+            if (!ReadFully(liFd, lpDst, luTake, luOffset - luPartStart))
+                return false;
             lpDst += luTake;
             luOffset += luTake;
             luSize -= luTake;
@@ -270,15 +514,19 @@ bool CArk::ReadImageRange(std::vector<FILE*>& lFiles, uint64_t luOffset, uint64_
     return luSize == 0;
 }
 
-// Extraction is a three-stage host pipeline around the GPU batch, on a small ring of pinned slots
-// instead of the reference's one archive-sized buffer (CArk.cpp:431, :738) and its serial
-// one-file-at-a-time writes (:435-501):
-//   reader thread   the image range a group of entries spans: part files -> the slot's source buffer
-//   this thread     ONE mod_cycle_batch per group (itself an overlapped upload / kernel / download)
-//                   from the slot's source buffer into its byte-packed staging buffer
-//   writer threads  create directories and write the group's files, then hand the slot back
-// so disk reads, PCIe, the kernel and disk writes overlap, and pinned memory is O(slots), not
-// O(archive).
+// Extraction streams the archive through a ring of slots instead of the reference's one archive-sized
+// buffer (CArk.cpp:431, :738) and its serial one-file-at-a-time writes (:435-501):
+//   * the file table becomes ONE descriptor plan (mod_plan_create: one tile map for the whole archive,
+//     on every GPU in use), the entries ordered by image offset and cut into ~32 MiB groups;
+//   * reader threads pread the image range of a group from the part files into the slot's pinned buffer;
+//   * this thread only ENQUEUES, per group and never waiting: upload of the range, the batched kernel over
+//     the group's tile sub-range (mod_plan_run_window: gather + per-entry Cycle into a byte-packed
+//     staging window), download -- on the slot's own stream, slots (and GPUs) taking groups in turn;
+//   * writer threads wait for the slot's stream, create directories and write the group's files, then
+//     hand the slot back.
+// Disk reads, PCIe both ways, the kernel and disk writes all overlap; pinned memory and HBM are
+// O(slots), not O(archive).  Entries that share an output name are resolved up front to the one whose
+// bytes the reference's in-order loop would leave on disk.
 eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTargetDirectory)
 {
     (void)liFirstFileIndex;  // the reference ignores both and walks the whole table (CArk.cpp:435)
@@ -286,14 +534,13 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
     if (mHeader.maFiles.empty())
         return eError_NoData;
     const double ldStart = NowSeconds();
+    const std::string lTarget = lpTargetDirectory;
 
     uint64_t luImageSize = 0;
     for (const modark::PartDef& lPart : mHeader.maParts)
         luImageSize += lPart.muSize;
 
-    // validate, then order the entries by where they sit in the image
     const size_t liCount = mHeader.maFiles.size();
-    std::vector<uint32_t> laOrder(liCount);
     for (size_t ii = 0; ii < liCount; ++ii) {
         const modark::FileDef& lFile = mHeader.maFiles[ii];
         if ((uint64_t)lFile.mi64Offset > luImageSize || (uint64_t)lFile.miSize > luImageSize - (uint64_t)lFile.mi64Offset) {
@@ -301,121 +548,131 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
             eError leError = eError_InvalidData;
             SHOW_ERROR_AND_RETURN;
         }
-        laOrder[ii] = (uint32_t)ii;
     }
+
+    // Duplicate output names.  The reference writes in table order, one file at a time (CArk.cpp:435-501):
+    // with overwriting on (the default) the LAST entry of a name is what stays on disk; with it off a
+    // file is only rewritten while it is still empty, so the FIRST non-empty entry stays.  Resolve that
+    // here so that exactly one entry per name is extracted, whatever order the pipeline writes in.
+    std::vector<uint32_t> laWinners;
+    {
+        std::unordered_map<std::string, uint32_t> lByName;  // name -> position in laWinners
+        laWinners.reserve(liCount);
+        for (size_t ii = 0; ii < liCount; ++ii) {
+            const modark::FileDef& lFile = mHeader.maFiles[ii];
+            const auto lFound = lByName.find(lFile.mName);
+            if (lFound == lByName.end()) {
+                lByName.emplace(lFile.mName, (uint32_t)laWinners.size());
+                laWinners.push_back((uint32_t)ii);
+                continue;
+            }
+            uint32_t& luWinner = laWinners[lFound->second];
+            if (CSettings::mbOverwriteOutputFiles || mHeader.maFiles[luWinner].miSize == 0)
+                luWinner = (uint32_t)ii;
+            VERBOSE_OUT("Duplicate entry " << lFile.mName.c_str() << "\n");
+        }
+    }
+
+    // order by where the entries sit in the image; groups of consecutive entries (~32 MiB of payload each)
+    std::vector<uint32_t> laOrder = laWinners;
     std::stable_sort(laOrder.begin(), laOrder.end(), [&](uint32_t a, uint32_t b) {
         return mHeader.maFiles[a].mi64Offset < mHeader.maFiles[b].mi64Offset;
     });
-
-    // groups of consecutive entries (~32 MiB of payload each) and the image range each one spans
     struct Group {
-        size_t first, last;           // positions in laOrder
-        uint64_t srcLo, srcHi;        // image range
-        uint64_t payload;
+        size_t first, last;     // positions in laOrder
+        uint64_t srcLo, srcHi;  // image range
+        uint64_t dstLo, dstHi;  // range of the byte-packed staging space
     };
     const uint64_t kuGroupBytes = 32ull << 20;
     std::vector<Group> laGroups;
-    uint64_t luMaxRange = 1, luMaxPayload = 1;
-    for (size_t liFirst = 0; liFirst < liCount;) {
-        Group lGroup{liFirst, liFirst, UINT64_MAX, 0, 0};
-        while (lGroup.last < liCount && (lGroup.payload < kuGroupBytes || lGroup.last == liFirst)) {
+    std::vector<mod_desc> laDescs(laOrder.size());
+    uint64_t luMaxRange = 1, luMaxPayload = 1, luStaged = 0;
+    bool lbAnyKey = false;
+    for (size_t liFirst = 0; liFirst < laOrder.size();) {
+        Group lGroup{liFirst, liFirst, UINT64_MAX, 0, luStaged, luStaged};
+        while (lGroup.last < laOrder.size() && (lGroup.dstHi - lGroup.dstLo < kuGroupBytes || lGroup.last == liFirst)) {
             const modark::FileDef& lFile = mHeader.maFiles[laOrder[lGroup.last]];
             if (lFile.miSize) {
                 lGroup.srcLo = std::min(lGroup.srcLo, (uint64_t)lFile.mi64Offset);
                 lGroup.srcHi = std::max(lGroup.srcHi, (uint64_t)lFile.mi64Offset + (uint64_t)lFile.miSize);
             }
-            lGroup.payload += (uint64_t)lFile.miSize;
+            const int liKey = EntryKey(laOrder[lGroup.last]);
+            lbAnyKey = lbAnyKey || (liKey % 0x7FFFFFFF) != 0;
+            laDescs[lGroup.last] = mod_desc{(uint64_t)lFile.mi64Offset, lGroup.dstHi, (uint32_t)lFile.miSize, liKey};
+            lGroup.dstHi += (uint64_t)lFile.miSize;
             ++lGroup.last;
         }
         if (lGroup.srcLo == UINT64_MAX)
             lGroup.srcLo = lGroup.srcHi = 0;
+        luStaged = lGroup.dstHi;
         luMaxRange = std::max(luMaxRange, lGroup.srcHi - lGroup.srcLo);
-        luMaxPayload = std::max(luMaxPayload, lGroup.payload);
+        luMaxPayload = std::max(luMaxPayload, lGroup.dstHi - lGroup.dstLo);
         laGroups.push_back(lGroup);
         liFirst = lGroup.last;
     }
 
-    // the ring of pinned slots
-    constexpr int kiSlots = 3;
-    enum eSlotState { eSlot_Free, eSlot_Filled, eSlot_Busy };
-    struct Slot {
-        unsigned char* mpSource = nullptr;
-        unsigned char* mpStaging = nullptr;
-        eSlotState meState = eSlot_Free;
+    // slots on every GPU in use, and the archive's plan on each of them
+    const int liOriginalDevice = mod_current_device();
+    const std::vector<int> laDevices = FacadeDevices(luStaged);
+    SlotRing lRing;
+    std::vector<mod_plan*> laPlans(laDevices.size(), nullptr);
+    auto lCleanup = [&]() {
+        lRing.Release();
+        for (mod_plan* lpPlan : laPlans)
+            mod_plan_destroy(lpPlan);
+        if (liOriginalDevice >= 0)
+            mod_init(liOriginalDevice);
     };
-    Slot laSlots[kiSlots];
-    const int liSlotsUsed = (int)std::min<size_t>(kiSlots, laGroups.size());
-    for (int ii = 0; ii < liSlotsUsed; ++ii) {
-        laSlots[ii].mpSource = (unsigned char*)mod_host_alloc(luMaxRange);
-        laSlots[ii].mpStaging = (unsigned char*)mod_host_alloc(luMaxPayload);
-    }
-    auto lFreeSlots = [&]() {
-        for (Slot& lSlot : laSlots) {
-            mod_host_free(lSlot.mpSource);
-            mod_host_free(lSlot.mpStaging);
-        }
-    };
-    for (int ii = 0; ii < liSlotsUsed; ++ii) {
-        if (!laSlots[ii].mpSource || !laSlots[ii].mpStaging) {
-            std::cout << "Failed to allocate pinned staging memory: " << mod_last_error() << "\n";
-            lFreeSlots();
-            return eError_NoData;
-        }
+    bool lbReady = lRing.Allocate(laDevices, 3, laGroups.size(), luMaxRange, luMaxPayload, true);
+    for (size_t dd = 0; dd < laDevices.size() && lbReady; ++dd)
+        lbReady = mod_init(laDevices[dd]) == MOD_OK &&
+                  mod_plan_create(laDescs.data(), laDescs.size(), luImageSize, luStaged, 0, &laPlans[dd]) == MOD_OK;
+    if (!lbReady) {
+        std::cout << "GPU extract could not be set up: " << mod_last_error() << "\n";
+        lCleanup();
+        return eError_NoData;
     }
     const double ldAllocated = NowSeconds();
 
-    std::mutex lMutex;
-    std::condition_variable lSignal;
-    std::atomic<int> liError{(int)eError_NoError};
-    auto lFail = [&](eError leWhat) {
-        int liExpected = (int)eError_NoError;
-        liError.compare_exchange_strong(liExpected, (int)leWhat);
-        lSignal.notify_all();
-    };
-    auto lWaitFor = [&](Slot& lSlot, eSlotState leWanted) {
-        std::unique_lock<std::mutex> lLock(lMutex);
-        lSignal.wait(lLock, [&]() { return lSlot.meState == leWanted || liError.load() != (int)eError_NoError; });
-        return liError.load() == (int)eError_NoError;
-    };
-    auto lSetState = [&](Slot& lSlot, eSlotState leState) {
+    const int liCores = HostThreads();
+    TaskPool lReaders(std::max(1, std::min(4, liCores / 4)));
+    TaskPool lWriters(std::max(2, std::min(8, liCores / 2)));
+    std::vector<int> laPartFds(mHeader.maParts.size(), -1);
+
+    // stage 1 (reader threads): the image range of a group, in pieces
+    auto lStartFill = [&](size_t gg) {
+        const Group& lGroup = laGroups[gg];
+        Slot& lSlot = lRing.maSlots[gg % lRing.maSlots.size()];
+        const uint64_t kuPiece = 8ull << 20;
+        const uint64_t luRange = lGroup.srcHi - lGroup.srcLo;
+        const int liPieces = (int)std::max<uint64_t>(1, (luRange + kuPiece - 1) / kuPiece);
         {
-            std::lock_guard<std::mutex> lLock(lMutex);
-            lSlot.meState = leState;
+            std::lock_guard<std::mutex> lLock(lRing.mMutex);
+            lSlot.meState = Slot::eFilling;
+            lSlot.miFillLeft = liPieces;
         }
-        lSignal.notify_all();
+        for (int pp = 0; pp < liPieces; ++pp) {
+            lReaders.Push([&, pp, luRange, kuPiece]() {
+                const uint64_t luLo = (uint64_t)pp * kuPiece, luHi = std::min(luRange, luLo + kuPiece);
+                // the range keeps its (offset & 15) phase inside the pinned buffer, like on the device
+                if (!lRing.Failed() && luHi > luLo &&
+                    !ReadImageRange(laPartFds, lGroup.srcLo + luLo, luHi - luLo, lSlot.mpHostIn + (lGroup.srcLo & 15u) + luLo))
+                    lRing.Fail(eError_FailedToOpenFile);
+                lRing.FillDone(lSlot);
+            });
+        }
     };
 
-    // stage 1: reader
-    std::thread lReader([&]() {
-        std::vector<FILE*> lFiles(mHeader.maParts.size(), nullptr);
-        for (size_t gg = 0; gg < laGroups.size(); ++gg) {
-            Slot& lSlot = laSlots[gg % kiSlots];
-            if (!lWaitFor(lSlot, eSlot_Free))
-                break;
-            const Group& lGroup = laGroups[gg];
-            if (!ReadImageRange(lFiles, lGroup.srcLo, lGroup.srcHi - lGroup.srcLo, lSlot.mpSource)) {
-                lFail(eError_FailedToOpenFile);
-                break;
-            }
-            lSetState(lSlot, eSlot_Filled);
+    // stage 3 (writer threads): the files of a group, a few dozen per task
+    auto lWriteFiles = [&](size_t gg, size_t liFrom, size_t liTo) {
+        const Group& lGroup = laGroups[gg];
+        Slot& lSlot = lRing.maSlots[gg % lRing.maSlots.size()];
+        thread_local std::unordered_set<std::string> lKnownDirectories;
+        if (!lRing.Failed() && lSlot.mbUsedGpu && mod_stream_sync(lSlot.mpStream) != MOD_OK) {
+            std::cout << "GPU extract failed: " << mod_last_error() << "\n";
+            lRing.Fail(eError_InvalidData);
         }
-        for (FILE* lpFile : lFiles)
-            if (lpFile)
-                std::fclose(lpFile);
-    });
-
-    // stage 3: writers
-    struct Job {
-        size_t group;
-        std::vector<uint64_t> offsets;  // staging offset of every entry of the group
-    };
-    std::deque<Job> lJobs;
-    bool lbNoMoreJobs = false;
-    const std::string lTarget = lpTargetDirectory;
-    auto lWriteGroup = [&](const Job& lJob) {
-        const Group& lGroup = laGroups[lJob.group];
-        Slot& lSlot = laSlots[lJob.group % kiSlots];
-        for (size_t ii = lGroup.first; ii < lGroup.last; ++ii) {
+        for (size_t ii = liFrom; ii < liTo && !lRing.Failed(); ++ii) {
             const modark::FileDef& lFile = mHeader.maFiles[laOrder[ii]];
             const std::string lOutputPath = lTarget + lFile.mName;
             if (EscapesTarget(lFile.mName)) {
@@ -426,96 +683,95 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
                 VERBOSE_OUT("Output file already exists, skipping: " << lOutputPath.c_str() << "\n");
                 continue;
             }
-            if (!MakeParentDirectories(lOutputPath)) {
-                lFail(eError_FailedToCreateDirectory);
-                return;
+            if (!MakeParentDirectoriesCached(lOutputPath, lKnownDirectories)) {
+                lRing.Fail(eError_FailedToCreateDirectory);
+                break;
             }
-            FILE* lpOutputFile = std::fopen(lOutputPath.c_str(), "wb");
-            if (!lpOutputFile) {
+            const int liFd = open(lOutputPath.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+            if (liFd < 0) {
                 std::cout << "Failed to create " << lOutputPath.c_str() << "\n";  // the reference carries on too (CArk.cpp:488-491)
                 continue;
             }
-            const size_t liWritten =
-                lFile.miSize ? std::fwrite(lSlot.mpStaging + lJob.offsets[ii - lGroup.first], 1, (size_t)lFile.miSize, lpOutputFile) : 0;
-            std::fclose(lpOutputFile);
-            if (liWritten != (size_t)lFile.miSize) {
-                lFail(eError_FailedToWriteData);
-                return;
-            }
+            const unsigned char* lpBytes = lSlot.mpHostOut + (lGroup.dstLo & 15u) + (laDescs[ii].dst_off - lGroup.dstLo);
+            const bool lbOk = lFile.miSize == 0 || WriteFully(liFd, lpBytes, (uint64_t)lFile.miSize, 0);
+            close(liFd);
+            if (!lbOk)
+                lRing.Fail(eError_FailedToWriteData);
         }
+        lRing.DrainDone(lSlot);
     };
-    auto lWriterLoop = [&]() {
-        for (;;) {
-            Job lJob;
-            {
-                std::unique_lock<std::mutex> lLock(lMutex);
-                lSignal.wait(lLock, [&]() { return !lJobs.empty() || lbNoMoreJobs; });
-                if (lJobs.empty())
-                    return;
-                lJob = std::move(lJobs.front());
-                lJobs.pop_front();
-            }
-            if (liError.load() == (int)eError_NoError)
-                lWriteGroup(lJob);
-            lSetState(laSlots[lJob.group % kiSlots], eSlot_Free);
-        }
-    };
-    std::vector<std::thread> laWriters;
-    for (int ii = 0; ii < 3; ++ii)
-        laWriters.emplace_back(lWriterLoop);
 
-    // stage 2: one GPU batch per group, file table -> device descriptors
-    std::vector<mod_desc> laDescs;
-    for (size_t gg = 0; gg < laGroups.size(); ++gg) {
-        const Group& lGroup = laGroups[gg];
-        Slot& lSlot = laSlots[gg % kiSlots];
-        if (!lWaitFor(lSlot, eSlot_Filled))
-            break;
-        Job lJob;
-        lJob.group = gg;
-        laDescs.clear();
-        uint64_t luOut = 0;
-        for (size_t ii = lGroup.first; ii < lGroup.last; ++ii) {
-            const modark::FileDef& lFile = mHeader.maFiles[laOrder[ii]];
-            mod_desc lDesc;
-            lDesc.src_off = lFile.miSize ? (uint64_t)lFile.mi64Offset - lGroup.srcLo : 0;
-            lDesc.dst_off = luOut;
-            lDesc.len = (uint32_t)lFile.miSize;
-            lDesc.key = EntryKey(laOrder[ii]);
-            laDescs.push_back(lDesc);
-            lJob.offsets.push_back(luOut);
-            luOut += (uint64_t)lFile.miSize;
-        }
-        if (luOut && mod_cycle_batch(laDescs.data(), laDescs.size(), lSlot.mpSource, lGroup.srcHi - lGroup.srcLo,
-                                     lSlot.mpStaging, luOut) != MOD_OK) {
-            std::cout << "GPU extract failed: " << mod_last_error() << "\n";
-            lFail(eError_InvalidData);
-            break;
-        }
+    // stage 2 (this thread): enqueue upload -> kernel -> download per group, never waiting for the GPU
+    size_t liNextFill = 0, liNextGpu = 0;
+    while (liNextGpu < laGroups.size() && !lRing.Failed()) {
         {
-            std::lock_guard<std::mutex> lLock(lMutex);
-            lSlot.meState = eSlot_Busy;
-            lJobs.push_back(std::move(lJob));
+            std::unique_lock<std::mutex> lLock(lRing.mMutex);
+            lRing.mSignal.wait(lLock, [&]() {
+                const bool lbCanFill = liNextFill < laGroups.size() && liNextFill < liNextGpu + lRing.maSlots.size() &&
+                                       lRing.maSlots[liNextFill % lRing.maSlots.size()].meState == Slot::eFree;
+                const bool lbCanRun = lRing.maSlots[liNextGpu % lRing.maSlots.size()].meState == Slot::eFilled && liNextGpu < liNextFill;
+                return lbCanFill || lbCanRun || lRing.Failed();
+            });
         }
-        lSignal.notify_all();
+        if (lRing.Failed())
+            break;
+        while (liNextFill < laGroups.size() && liNextFill < liNextGpu + lRing.maSlots.size() &&
+               lRing.maSlots[liNextFill % lRing.maSlots.size()].meState == Slot::eFree)
+            lStartFill(liNextFill++);
+        while (liNextGpu < liNextFill && lRing.maSlots[liNextGpu % lRing.maSlots.size()].meState == Slot::eFilled) {
+            const size_t gg = liNextGpu++;
+            const Group& lGroup = laGroups[gg];
+            Slot& lSlot = lRing.maSlots[gg % lRing.maSlots.size()];
+            const uint64_t luRange = lGroup.srcHi - lGroup.srcLo, luPayload = lGroup.dstHi - lGroup.dstLo;
+            lSlot.mbUsedGpu = luPayload != 0;
+            if (luPayload) {
+                size_t liDeviceIndex = 0;
+                while (laDevices[liDeviceIndex] != lSlot.miDevice)
+                    ++liDeviceIndex;
+                uint64_t luTile0 = 0, luTile1 = 0;
+                unsigned char* lpDevIn = (unsigned char*)lSlot.mpDevIn + (lGroup.srcLo & 15u);
+                unsigned char* lpDevOut = (unsigned char*)lSlot.mpDevOut + (lGroup.dstLo & 15u);
+                const bool lbOk =
+                    mod_init(lSlot.miDevice) == MOD_OK &&
+                    mod_plan_tile_range(laPlans[liDeviceIndex], lGroup.first, lGroup.last, &luTile0, &luTile1) == MOD_OK &&
+                    mod_memcpy_h2d(lpDevIn, lSlot.mpHostIn + (lGroup.srcLo & 15u), luRange, lSlot.mpStream) == MOD_OK &&
+                    mod_plan_run_window(laPlans[liDeviceIndex], luTile0, luTile1, lpDevIn, lGroup.srcLo, luRange, lpDevOut,
+                                        lGroup.dstLo, luPayload, lSlot.mpStream) == MOD_OK &&
+                    mod_memcpy_d2h(lSlot.mpHostOut + (lGroup.dstLo & 15u), lpDevOut, luPayload, lSlot.mpStream) == MOD_OK;
+                if (!lbOk) {
+                    std::cout << "GPU extract failed: " << mod_last_error() << "\n";
+                    lRing.Fail(eError_InvalidData);
+                    break;
+                }
+            }
+            const size_t kiFilesPerTask = 48;
+            const size_t liFiles = lGroup.last - lGroup.first;
+            const int liTasks = (int)std::max<size_t>(1, (liFiles + kiFilesPerTask - 1) / kiFilesPerTask);
+            {
+                std::lock_guard<std::mutex> lLock(lRing.mMutex);
+                lSlot.meState = Slot::eDraining;
+                lSlot.miDrainLeft = liTasks;
+            }
+            for (int tt = 0; tt < liTasks; ++tt) {
+                const size_t liFrom = lGroup.first + (size_t)tt * kiFilesPerTask;
+                lWriters.Push([&, gg, liFrom, liTo = std::min(lGroup.last, liFrom + kiFilesPerTask)]() { lWriteFiles(gg, liFrom, liTo); });
+            }
+        }
     }
-    {
-        std::lock_guard<std::mutex> lLock(lMutex);
-        lbNoMoreJobs = true;
-    }
-    lSignal.notify_all();
-    const double ldGpuDone = NowSeconds();
-    lReader.join();
-    for (std::thread& lWriter : laWriters)
-        lWriter.join();
+    const double ldEnqueued = NowSeconds();
+    lReaders.Finish();
+    lWriters.Finish();
     const double ldWritten = NowSeconds();
-    lFreeSlots();
+    for (int liFd : laPartFds)
+        if (liFd >= 0)
+            close(liFd);
+    lCleanup();
     if (TraceEnabled())
-        std::fprintf(stderr, "[mod] ExtractFiles: %zu groups, pinned slots %.3f s, read+GPU %.3f s, writers drain %.3f s, free %.3f s\n",
-                     laGroups.size(), ldAllocated - ldStart, ldGpuDone - ldAllocated, ldWritten - ldGpuDone,
-                     NowSeconds() - ldWritten);
+        std::fprintf(stderr, "[mod] ExtractFiles: %zu groups on %zu GPU(s), %zu slots; setup %.3f s, pipeline %.3f s, drain %.3f s, free %.3f s\n",
+                     laGroups.size(), laDevices.size(), (size_t)std::min<size_t>(laGroups.size(), 3 * laDevices.size()),
+                     ldAllocated - ldStart, ldEnqueued - ldAllocated, ldWritten - ldEnqueued, NowSeconds() - ldWritten);
 
-    eError leError = (eError)liError.load();
+    eError leError = (eError)lRing.miError.load();
     SHOW_ERROR_AND_RETURN;
     return eError_NoError;
 }
@@ -604,44 +860,34 @@ eError CArk::ConstructFromDirectory(const char* lpInputDirectory, const CArk& lR
     return eError_NoError;
 }
 
+// BuildArk assigns every entry its byte-packed offset and closes the parts (reference CArk.cpp:760-828)
+// from the SIZES alone; the payload itself is never gathered into one archive-sized buffer
+// (CArk.cpp:769-811 does): SaveArk streams it from the input files straight into the part files.
 eError CArk::BuildArk(const char* lpInputDirectory, std::vector<SSongConfig> laSongs)
 {
     (void)laSongs;  // the reference appends its four defaults and never reads them here (CArk.cpp:762-765)
     VERBOSE_OUT("Building ark\n");
     if (mHeader.maParts.empty())
         return eError_NoData;
-
-    uint64_t luTotalArkSize = 0;
-    for (const modark::FileDef& lFile : mHeader.maFiles)
-        luTotalArkSize += (uint64_t)lFile.miSize;
     ReleaseArkData();
-    mpArkData = (unsigned char*)mod_host_alloc(luTotalArkSize + 1);
-    if (!mpArkData) {
-        std::cout << "Failed to allocate pinned memory for the archive: " << mod_last_error() << "\n";
-        return eError_NoData;
-    }
-    muArkDataSize = luTotalArkSize;
+    mBuildInputDirectory = lpInputDirectory;
 
-    // pass 1 (serial, sizes only): byte-packed running offsets and part sizes
-    std::string lRoot = lpInputDirectory;
     size_t liArkIndex = 0;
     int64_t li64Allowed = mHeader.maParts[0].muSize;
     uint64_t luPtr = 0, luPartStart = 0;
-    std::vector<mod_desc> laDescs;
-    std::vector<size_t> laToRead;
-    bool lbAnyKey = false;
     for (size_t ii = 0; ii < mHeader.maFiles.size(); ++ii) {
         modark::FileDef& lFile = mHeader.maFiles[ii];
         if (lFile.miSize == 0) {
             lFile.mi64Offset = 0;
             continue;
         }
+        // the reference opens (and reads) the file here and gives up on the first one it cannot open
+        if (access((mBuildInputDirectory + lFile.mName).c_str(), R_OK) != 0) {
+            eError leError = eError_FailedToOpenFile;
+            SHOW_ERROR_AND_RETURN;
+        }
         // scatter: the file lands at the running, byte-packed offset
         lFile.mi64Offset = (int64_t)luPtr;
-        laToRead.push_back(ii);
-        const int liKey = EntryKey(ii);
-        lbAnyKey = lbAnyKey || (liKey % 0x7FFFFFFF) != 0;
-        laDescs.push_back(mod_desc{luPtr, luPtr, (uint32_t)lFile.miSize, liKey});
         luPtr += (uint64_t)lFile.miSize;
 
         // a part closes once it EXCEEDS its allowance; the overshoot shortens the next allowance
@@ -661,51 +907,206 @@ eError CArk::BuildArk(const char* lpInputDirectory, std::vector<SSongConfig> laS
         }
     }
     mHeader.maParts[liArkIndex].muSize = (unsigned int)(luPtr - luPartStart);
-
-    // pass 2: the payload reads (the reference's one fread per file, CArk.cpp:796-811) fanned out over
-    // a few threads -- thousands of small files are latency-bound on any real file system
-    std::atomic<size_t> liNext{0};
-    std::atomic<bool> lbOpenFailed{false};
-    auto lReadFiles = [&]() {
-        for (;;) {
-            const size_t liSlot = liNext.fetch_add(1);
-            if (liSlot >= laToRead.size() || lbOpenFailed.load())
-                return;
-            const modark::FileDef& lFile = mHeader.maFiles[laToRead[liSlot]];
-            FILE* lpInputFile = std::fopen((lRoot + lFile.mName).c_str(), "rb");
-            if (!lpInputFile) {
-                lbOpenFailed.store(true);
-                return;
-            }
-            unsigned char* lpDst = mpArkData + lFile.mi64Offset;
-            const size_t liRead = std::fread(lpDst, 1, (size_t)lFile.miSize, lpInputFile);
-            std::fclose(lpInputFile);
-            if (liRead != (size_t)lFile.miSize)
-                std::memset(lpDst + liRead, 0, (size_t)lFile.miSize - liRead);
-        }
-    };
-    {
-        std::vector<std::thread> laReaders;
-        for (int ii = 0; ii < 3; ++ii)
-            laReaders.emplace_back(lReadFiles);
-        lReadFiles();
-        for (std::thread& lThread : laReaders)
-            lThread.join();
-    }
-    if (lbOpenFailed.load()) {
-        eError leError = eError_FailedToOpenFile;
-        SHOW_ERROR_AND_RETURN;
-    }
-
-    // entries that carry a key are ciphered where they lie, all in one batched launch
-    if (lbAnyKey && !laDescs.empty()) {
-        if (mod_cycle_batch(laDescs.data(), laDescs.size(), mpArkData, muArkDataSize, mpArkData, muArkDataSize) != MOD_OK) {
-            std::cout << "GPU build failed: " << mod_last_error() << "\n";
-            return eError_InvalidData;
-        }
-    }
+    muBuiltImageSize = luPtr;
+    mbBuilt = true;
     VERBOSE_OUT("Ark built\n");
     return eError_NoError;
+}
+
+// Stream the image BuildArk laid out into the part files: reader threads load the input files of a
+// ~32 MiB group into a pinned slot, entries that carry a key are ciphered on the GPU (upload, one
+// mod_plan_run_window over the group's tiles of the archive-wide plan, download -- enqueued on the
+// slot's stream, never waited for here), writer threads pwrite the group's byte range into the part
+// file(s) it falls in.  With all keys 0 (the reference never ciphers ARK bodies) the GPU is not
+// involved and the bytes go from the read buffer straight to the part files.
+eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
+{
+    const double ldStart = NowSeconds();
+    // non-empty entries in table order == image order
+    std::vector<uint32_t> laOrder;
+    std::vector<mod_desc> laDescs;
+    bool lbAnyKey = false;
+    for (size_t ii = 0; ii < mHeader.maFiles.size(); ++ii) {
+        const modark::FileDef& lFile = mHeader.maFiles[ii];
+        if (lFile.miSize == 0)
+            continue;
+        const int liKey = EntryKey(ii);
+        lbAnyKey = lbAnyKey || (liKey % 0x7FFFFFFF) != 0;
+        laOrder.push_back((uint32_t)ii);
+        laDescs.push_back(mod_desc{(uint64_t)lFile.mi64Offset, (uint64_t)lFile.mi64Offset, (uint32_t)lFile.miSize, liKey});
+    }
+    if (laOrder.empty())
+        return eError_NoError;
+
+    struct Group {
+        size_t first, last;  // positions in laOrder
+        uint64_t lo, hi;     // image range
+    };
+    const uint64_t kuGroupBytes = 32ull << 20;
+    std::vector<Group> laGroups;
+    uint64_t luMaxRange = 1;
+    for (size_t liFirst = 0; liFirst < laOrder.size();) {
+        Group lGroup{liFirst, liFirst, laDescs[liFirst].src_off, laDescs[liFirst].src_off};
+        while (lGroup.last < laOrder.size() && (lGroup.hi - lGroup.lo < kuGroupBytes || lGroup.last == liFirst)) {
+            lGroup.hi = laDescs[lGroup.last].src_off + laDescs[lGroup.last].len;
+            ++lGroup.last;
+        }
+        luMaxRange = std::max(luMaxRange, lGroup.hi - lGroup.lo);
+        laGroups.push_back(lGroup);
+        liFirst = lGroup.last;
+    }
+
+    const int liOriginalDevice = lbAnyKey ? mod_current_device() : -1;
+    const std::vector<int> laDevices = lbAnyKey ? FacadeDevices(muBuiltImageSize) : std::vector<int>{0};
+    SlotRing lRing;
+    std::vector<mod_plan*> laPlans(laDevices.size(), nullptr);
+    auto lCleanup = [&]() {
+        lRing.Release();
+        for (mod_plan* lpPlan : laPlans)
+            mod_plan_destroy(lpPlan);
+        if (liOriginalDevice >= 0)
+            mod_init(liOriginalDevice);
+    };
+    bool lbReady = lRing.Allocate(laDevices, 3, laGroups.size(), luMaxRange, lbAnyKey ? luMaxRange : 0, lbAnyKey);
+    for (size_t dd = 0; dd < laDevices.size() && lbReady && lbAnyKey; ++dd)
+        lbReady = mod_init(laDevices[dd]) == MOD_OK &&
+                  mod_plan_create(laDescs.data(), laDescs.size(), muBuiltImageSize, muBuiltImageSize, 0, &laPlans[dd]) == MOD_OK;
+    if (!lbReady) {
+        std::cout << "GPU build could not be set up: " << mod_last_error() << "\n";
+        lCleanup();
+        return eError_NoData;
+    }
+
+    const int liCores = HostThreads();
+    TaskPool lReaders(std::max(2, std::min(8, liCores / 2)));
+    TaskPool lWriters(std::max(1, std::min(4, liCores / 4)));
+
+    // stage 1 (reader threads): the input files of a group, a few dozen per task (the reference's one
+    // fread per file, CArk.cpp:796-811 -- thousands of small files are latency-bound on any file system)
+    auto lReadFiles = [&](size_t gg, size_t liFrom, size_t liTo) {
+        const Group& lGroup = laGroups[gg];
+        Slot& lSlot = lRing.maSlots[gg % lRing.maSlots.size()];
+        for (size_t ii = liFrom; ii < liTo && !lRing.Failed(); ++ii) {
+            const modark::FileDef& lFile = mHeader.maFiles[laOrder[ii]];
+            const int liFd = open((mBuildInputDirectory + lFile.mName).c_str(), O_RDONLY);
+            if (liFd < 0) {
+                lRing.Fail(eError_FailedToOpenFile);
+                break;
+            }
+            unsigned char* lpDst = lSlot.mpHostIn + (lGroup.lo & 15u) + ((uint64_t)lFile.mi64Offset - lGroup.lo);
+            const bool lbOk = ReadFully(liFd, lpDst, (uint64_t)lFile.miSize, 0);  // a file that shrank reads as zeros
+            close(liFd);
+            if (!lbOk)
+                lRing.Fail(eError_FailedToOpenFile);
+        }
+        lRing.FillDone(lSlot);
+    };
+    auto lStartFill = [&](size_t gg) {
+        const Group& lGroup = laGroups[gg];
+        Slot& lSlot = lRing.maSlots[gg % lRing.maSlots.size()];
+        const size_t kiFilesPerTask = 48;
+        const int liTasks = (int)((lGroup.last - lGroup.first + kiFilesPerTask - 1) / kiFilesPerTask);
+        {
+            std::lock_guard<std::mutex> lLock(lRing.mMutex);
+            lSlot.meState = Slot::eFilling;
+            lSlot.miFillLeft = liTasks;
+        }
+        for (int tt = 0; tt < liTasks; ++tt) {
+            const size_t liFrom = lGroup.first + (size_t)tt * kiFilesPerTask;
+            lReaders.Push([&, gg, liFrom, liTo = std::min(lGroup.last, liFrom + kiFilesPerTask)]() { lReadFiles(gg, liFrom, liTo); });
+        }
+    };
+
+    // stage 3 (writer threads): the group's byte range, cut where it crosses into another part file
+    auto lWriteRange = [&](size_t gg, size_t liTarget, uint64_t luLo, uint64_t luHi) {
+        const Group& lGroup = laGroups[gg];
+        Slot& lSlot = lRing.maSlots[gg % lRing.maSlots.size()];
+        if (!lRing.Failed() && lSlot.mbUsedGpu && mod_stream_sync(lSlot.mpStream) != MOD_OK) {
+            std::cout << "GPU build failed: " << mod_last_error() << "\n";
+            lRing.Fail(eError_InvalidData);
+        }
+        const unsigned char* lpBytes = (lSlot.mbUsedGpu ? lSlot.mpHostOut : lSlot.mpHostIn) + (lGroup.lo & 15u) + (luLo - lGroup.lo);
+        const PartTarget& lPart = laTargets[liTarget];
+        if (!lRing.Failed() && !WriteFully(lPart.miFd, lpBytes, luHi - luLo, luLo - lPart.muImageStart))
+            lRing.Fail(eError_FailedToWriteData);
+        lRing.DrainDone(lSlot);
+    };
+
+    // stage 2 (this thread)
+    size_t liNextFill = 0, liNextGpu = 0;
+    while (liNextGpu < laGroups.size() && !lRing.Failed()) {
+        {
+            std::unique_lock<std::mutex> lLock(lRing.mMutex);
+            lRing.mSignal.wait(lLock, [&]() {
+                const bool lbCanFill = liNextFill < laGroups.size() && liNextFill < liNextGpu + lRing.maSlots.size() &&
+                                       lRing.maSlots[liNextFill % lRing.maSlots.size()].meState == Slot::eFree;
+                const bool lbCanRun = liNextGpu < liNextFill && lRing.maSlots[liNextGpu % lRing.maSlots.size()].meState == Slot::eFilled;
+                return lbCanFill || lbCanRun || lRing.Failed();
+            });
+        }
+        if (lRing.Failed())
+            break;
+        while (liNextFill < laGroups.size() && liNextFill < liNextGpu + lRing.maSlots.size() &&
+               lRing.maSlots[liNextFill % lRing.maSlots.size()].meState == Slot::eFree)
+            lStartFill(liNextFill++);
+        while (liNextGpu < liNextFill && lRing.maSlots[liNextGpu % lRing.maSlots.size()].meState == Slot::eFilled) {
+            const size_t gg = liNextGpu++;
+            const Group& lGroup = laGroups[gg];
+            Slot& lSlot = lRing.maSlots[gg % lRing.maSlots.size()];
+            const uint64_t luRange = lGroup.hi - lGroup.lo;
+            lSlot.mbUsedGpu = lbAnyKey;
+            if (lbAnyKey) {
+                size_t liDeviceIndex = 0;
+                while (laDevices[liDeviceIndex] != lSlot.miDevice)
+                    ++liDeviceIndex;
+                uint64_t luTile0 = 0, luTile1 = 0;
+                unsigned char* lpDevIn = (unsigned char*)lSlot.mpDevIn + (lGroup.lo & 15u);
+                unsigned char* lpDevOut = (unsigned char*)lSlot.mpDevOut + (lGroup.lo & 15u);
+                const bool lbOk =
+                    mod_init(lSlot.miDevice) == MOD_OK &&
+                    mod_plan_tile_range(laPlans[liDeviceIndex], lGroup.first, lGroup.last, &luTile0, &luTile1) == MOD_OK &&
+                    mod_memcpy_h2d(lpDevIn, lSlot.mpHostIn + (lGroup.lo & 15u), luRange, lSlot.mpStream) == MOD_OK &&
+                    mod_plan_run_window(laPlans[liDeviceIndex], luTile0, luTile1, lpDevIn, lGroup.lo, luRange, lpDevOut, lGroup.lo,
+                                        luRange, lSlot.mpStream) == MOD_OK &&
+                    mod_memcpy_d2h(lSlot.mpHostOut + (lGroup.lo & 15u), lpDevOut, luRange, lSlot.mpStream) == MOD_OK;
+                if (!lbOk) {
+                    std::cout << "GPU build failed: " << mod_last_error() << "\n";
+                    lRing.Fail(eError_InvalidData);
+                    break;
+                }
+            }
+            // pieces of [lo, hi) per part file that receives them
+            struct Piece {
+                size_t target;
+                uint64_t lo, hi;
+            };
+            std::vector<Piece> laPieces;
+            for (size_t tt = 0; tt < laTargets.size(); ++tt) {
+                const uint64_t luLo = std::max(lGroup.lo, laTargets[tt].muImageStart);
+                const uint64_t luHi = std::min(lGroup.hi, laTargets[tt].muImageStart + laTargets[tt].muSize);
+                if (laTargets[tt].miFd >= 0 && luHi > luLo)
+                    laPieces.push_back(Piece{tt, luLo, luHi});
+            }
+            if (laPieces.empty()) {  // every part this group falls in was skipped (existing output kept)
+                lRing.Set(lSlot, Slot::eFree);
+                continue;
+            }
+            {
+                std::lock_guard<std::mutex> lLock(lRing.mMutex);
+                lSlot.meState = Slot::eDraining;
+                lSlot.miDrainLeft = (int)laPieces.size();
+            }
+            for (const Piece& lPiece : laPieces)
+                lWriters.Push([&, gg, lPiece]() { lWriteRange(gg, lPiece.target, lPiece.lo, lPiece.hi); });
+        }
+    }
+    lReaders.Finish();
+    lWriters.Finish();
+    lCleanup();
+    if (TraceEnabled())
+        std::fprintf(stderr, "[mod] SaveArk: streamed %zu groups (%s) in %.3f s\n", laGroups.size(),
+                     lbAnyKey ? "ciphered on the GPU" : "plain copy, no GPU", NowSeconds() - ldStart);
+    return (eError)lRing.miError.load();
 }
 
 eError CArk::SaveArk(const char* lpOutputDirectory, const char* lpHeaderFilename) const
@@ -735,28 +1136,47 @@ eError CArk::SaveArk(const char* lpOutputDirectory, const char* lpHeaderFilename
         }
     }
 
-    // parts: consecutive slices of the image
-    const unsigned char* lpArkPtr = mpArkData;
+    // parts: consecutive slices of the image.  Like the reference, the image cursor does not advance
+    // past a part that is skipped because its output already exists (CArk.cpp:863-868) or cannot be
+    // created (:880-897).
+    std::vector<PartTarget> laTargets;
+    uint64_t luCursor = 0;
     for (const modark::PartDef& lPart : mHeader.maParts) {
         const std::string lFilename = std::string(lpOutputDirectory) + lPart.mPath;
         if (KeepExistingOutput(lFilename)) {
             std::cout << "Output file already exists: " << lFilename.c_str() << "\n";
-            continue;  // like the reference, the cursor does not advance past a skipped part (CArk.cpp:863-868)
+            continue;
         }
         std::cout << "Writing " << lFilename.c_str() << "\n";
         MakeParentDirectories(lFilename);
-        FILE* lpOutputFile = std::fopen(lFilename.c_str(), "wb");
-        if (!lpOutputFile) {
+        PartTarget lTarget;
+        lTarget.miFd = open(lFilename.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (lTarget.miFd < 0) {
             std::cout << "Failed to open file for writing: " << lFilename.c_str() << "\n";
             continue;
         }
-        const size_t liWritten = (lPart.muSize && lpArkPtr) ? std::fwrite(lpArkPtr, 1, lPart.muSize, lpOutputFile) : 0;
-        std::fclose(lpOutputFile);
-        if (liWritten != lPart.muSize) {
-            eError leError = eError_FailedToWriteData;
-            SHOW_ERROR_AND_RETURN;
-        }
-        lpArkPtr += lPart.muSize;
+        lTarget.muImageStart = luCursor;
+        lTarget.muSize = lPart.muSize;
+        laTargets.push_back(lTarget);
+        luCursor += lPart.muSize;
     }
+
+    eError leError = eError_NoError;
+    if (mbBuilt) {
+        leError = StreamBuiltImage(laTargets);
+    } else if (mpArkData) {  // a loaded image (Load + LoadArkData) saved again
+        for (const PartTarget& lTarget : laTargets) {
+            const uint64_t luTake = lTarget.muImageStart < muArkDataSize ? std::min<uint64_t>(lTarget.muSize, muArkDataSize - lTarget.muImageStart) : 0;
+            if (luTake != lTarget.muSize || !WriteFully(lTarget.miFd, mpArkData + lTarget.muImageStart, luTake, 0))
+                leError = eError_FailedToWriteData;
+        }
+    } else {
+        for (const PartTarget& lTarget : laTargets)
+            if (lTarget.muSize)
+                leError = eError_FailedToWriteData;  // nothing to write the parts from
+    }
+    for (const PartTarget& lTarget : laTargets)
+        close(lTarget.miFd);
+    SHOW_ERROR_AND_RETURN;
     return eError_NoError;
 }

@@ -5,13 +5,14 @@
 //   Load                  reads the .hdr, deciphers it on the GPU (mod_cycle; reference call site
 //                         CArk.cpp:338-339) and parses it on the host (ArkHeader.cpp)
 //   LoadArkData           concatenates the .ark parts into one PINNED host image (CArk.cpp:723-758)
-//   ExtractFiles          turns the file table into mod_desc descriptors and gathers the entries
-//                         through the batched kernel (mod_cycle_batch; CArk.cpp:494) in a
-//                         reader -> GPU -> writer pipeline over a ring of pinned slots: part files
-//                         are still being read while earlier groups are on the GPU / being written
-//   BuildArk              byte-packs the input files into the image, assigns offsets and part sizes
-//                         (CArk.cpp:760-828) and, when entries carry keys, ciphers them in one batch
-//   SaveArk               serialises + enciphers the header (CArk.cpp:1135-1136) and writes the parts
+//   ExtractFiles          turns the file table into ONE descriptor plan (mod_plan_create) and gathers
+//                         the entries through the batched kernel group by group (mod_plan_run_window;
+//                         CArk.cpp:494) in a reader -> GPU -> writer pipeline over a ring of slots on
+//                         every visible GPU: nothing is ever waited for on the thread that enqueues
+//   BuildArk              assigns byte-packed offsets and part sizes from the file sizes (CArk.cpp:760-828)
+//   SaveArk               serialises + enciphers the header (CArk.cpp:1135-1136) and STREAMS the payload
+//                         from the input files into the part files through the same kind of slot ring
+//                         (entries that carry a key are ciphered on the GPU on the way)
 //
 // The reference never ciphers ARK bodies (SURVEY.md Finding 2): all entry keys default to 0, the
 // identity keystream, so the bytes produced are the reference's.  SetEntryKeys / SetUniformEntryKey
@@ -58,15 +59,25 @@ private:
     int EntryKey(size_t liIndex) const;
     eError AllocateArkData();
     eError ReadParts();
-    bool ReadImageRange(std::vector<FILE*>& lFiles, uint64_t luOffset, uint64_t luSize, unsigned char* lpDst) const;
+    bool ReadImageRange(std::vector<int>& laFds, uint64_t luOffset, uint64_t luSize, unsigned char* lpDst) const;
+    struct PartTarget {
+        int miFd = -1;             // part file open for writing
+        uint64_t muImageStart = 0; // first image byte it receives
+        uint64_t muSize = 0;
+    };
+    eError StreamBuiltImage(const std::vector<PartTarget>& laTargets) const;
     bool ShouldPackFile(const std::vector<SSongConfig>& laSongs, const char* lpFilename) const;
     void ReleaseArkData();
 
     modark::HeaderImage mHeader;
     bool mbLoaded = false;
 
-    unsigned char* mpArkData = nullptr;  // pinned host memory (mod_host_alloc)
+    unsigned char* mpArkData = nullptr;  // pinned host memory (mod_host_alloc), LoadArkData only
     uint64_t muArkDataSize = 0;
+
+    bool mbBuilt = false;                // BuildArk has laid the image out; SaveArk streams it
+    std::string mBuildInputDirectory;
+    uint64_t muBuiltImageSize = 0;
 
     std::vector<int> maEntryKeys;
     int miUniformKey = 0;

@@ -800,6 +800,19 @@ int mod_init(int device)
     return acquire(device, &c);
 }
 
+int mod_current_device(void)
+{
+    int cur = -1;
+    CUDA_TRY(cudaGetDevice(&cur));
+    return cur;
+}
+
+int mod_is_device_pointer(const void* p)
+{
+    int dev = -1;
+    return pointer_device(p, &dev) ? 1 : 0;
+}
+
 void mod_shutdown(void)
 {
     std::lock_guard<std::mutex> init_lock(g_init_mu);

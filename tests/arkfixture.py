@@ -26,9 +26,49 @@ def make_names(n: int, seed: int = 1) -> List[str]:
     return sorted(names)
 
 
+def cipher_entries(image: np.ndarray, offsets, sizes, key: int) -> None:
+    """In place: one Cycle() per entry with `key` -- the unmodified reference cipher over all host
+    threads when it is built (oracle/_ref), else the C restatement."""
+    import os as _os
+    if oracle.have_ref():
+        parts = np.zeros(len(sizes), dtype=oracle.PART_DTYPE)
+        parts["off"] = np.asarray(offsets, dtype=np.uint64)
+        parts["len"] = np.asarray(sizes, dtype=np.uint32)
+        parts["key"] = synth.i32(key)
+        oracle.ref_cycle_parts(image, parts, _os.cpu_count() or 1)
+    else:
+        for o, s in zip(offsets, sizes):
+            if s:
+                image[int(o):int(o) + int(s)] = oracle.cycle(image[int(o):int(o) + int(s)], key)
+
+
+def reconstruct_walk(names, by_name=None):
+    """Directory walk order of the facade's ConstructFromDirectory: per directory, files then
+    sub-directories, each in NTFS index order (by upper-cased name)."""
+    tree = {}
+    for n in names:
+        node = tree
+        parts = n.split("/")
+        for p in parts[:-1]:
+            node = node.setdefault(("d", p), {})
+        node[("f", parts[-1])] = n
+    out = []
+
+    def walk(node):
+        files = sorted([k for k in node if k[0] == "f"], key=lambda k: k[1].upper())
+        dirs = sorted([k for k in node if k[0] == "d"], key=lambda k: k[1].upper())
+        for k in files:
+            out.append(node[k])
+        for k in dirs:
+            walk(node[k])
+    walk(tree)
+    return out
+
+
 def write_archive(root: str, *, ps4: bool = True, n_files: int = 60, n_parts: int = 3, seed: int = 1,
-                  body_key: int = 0, sizes: Optional[Sequence[int]] = None):
-    """Write main_<plat>.hdr + part files under `root`.  Returns (Header, plain payload list)."""
+                  body_key: int = 0, sizes: Optional[Sequence[int]] = None, contents=None):
+    """Write main_<plat>.hdr + part files under `root`.  `contents` maps entry index -> bytes for
+    entries that must hold something specific (e.g. a DTB).  Returns (Header, plain payload list, plain header)."""
     os.makedirs(root, exist_ok=True)
     plat = "ps4" if ps4 else "ps3"
     rng = np.random.default_rng(seed)
@@ -40,12 +80,14 @@ def write_archive(root: str, *, ps4: bool = True, n_files: int = 60, n_parts: in
     offsets = synth.packed_offsets(np.array(sizes, dtype=np.int64))
     total = int(sum(sizes))
     payloads = [synth.payload(int(o) + 1000 * seed, int(s)).tobytes() for o, s in zip(offsets, sizes)]
-    image = bytearray(total)
-    for o, s, p in zip(offsets, sizes, payloads):
-        body = np.frombuffer(p, dtype=np.uint8)
-        if body_key and s:
-            body = oracle.cycle(body, body_key)
-        image[int(o):int(o) + s] = body.tobytes()
+    if contents:
+        for i, blob in contents.items():
+            assert len(blob) == sizes[i]
+            payloads[i] = blob
+    image = np.frombuffer(b"".join(payloads), dtype=np.uint8).copy()
+    if body_key and total:
+        cipher_entries(image, offsets, sizes, body_key)
+    image = image.tobytes()
     # parts: equal shares, the last takes the remainder
     share = total // n_parts
     part_sizes = [share] * (n_parts - 1) + [total - share * (n_parts - 1)]

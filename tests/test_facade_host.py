@@ -133,26 +133,7 @@ def test_pack_roundtrip_offsets_parts_and_header_bytes(cli, tmp_path, ps4):
     check_unpacked(tmp_path / "again" / "out", hdr, payloads)
 
 
-def reconstruct_walk(names, by_name):
-    """Directory walk order of the facade: per directory, files (case-insensitive) then sub-directories."""
-    tree = {}
-    for n in names:
-        node = tree
-        parts = n.split("/")
-        for p in parts[:-1]:
-            node = node.setdefault(("d", p), {})
-        node[("f", parts[-1])] = n
-    out = []
-
-    def walk(node):
-        files = sorted([k for k in node if k[0] == "f"], key=lambda k: k[1].lower())
-        dirs = sorted([k for k in node if k[0] == "d"], key=lambda k: k[1].lower())
-        for k in files:
-            out.append(node[k])
-        for k in dirs:
-            walk(node[k])
-    walk(tree)
-    return out
+reconstruct_walk = arkfixture.reconstruct_walk
 
 
 def test_pack_filters_unknown_files_and_songs(cli, tmp_path):
@@ -178,6 +159,40 @@ def test_pack_filters_unknown_files_and_songs(cli, tmp_path):
     new2, _ = arkfixture.read_header(str(tmp_path / "r2" / "main_ps4.hdr"))
     assert {e.name for e in new2.entries} == {e.name for e in hdr.entries} | {
         "ps4/brand_new.bin", "ps4/config/amp_config.dta_dta_ps4", "ps4/config/amp_songs_config.dta_dta_ps4"}
+
+
+def test_unpack_duplicate_names_resolve_in_table_order(cli, tmp_path):
+    """Two entries with one name: the reference writes in table order with overwriting on (its default,
+    CArk.cpp:435-501, Settings.cpp:7), so the LAST entry's bytes stay on disk -- whatever order the
+    pipeline's writer threads run in, and without two threads ever writing one path."""
+    first, second, other = b"F" * 70000, b"S" * 50000, b"o" * 1000
+    entries = [ao.Entry(name="ps4/dup.bin", offset=0, size=len(first)),
+               ao.Entry(name="ps4/other.bin", offset=len(first), size=len(other)),
+               ao.Entry(name="ps4/dup.bin", offset=len(first) + len(other), size=len(second)),
+               ao.Entry(name="ps4/empty_dup.bin", offset=0, size=0),
+               ao.Entry(name="ps4/empty_dup.bin", offset=0, size=0)]
+    image = first + other + second
+    hdr = ao.Header(ps4=True, parts=[("main_ps4_0.ark", len(image))], entries=entries)
+    plain = ao.serialise_header(hdr)
+    cipher = plain[:4] + oracle.cycle(np.frombuffer(plain[4:], dtype=np.uint8), ao.KEY_PS4).tobytes()
+    (tmp_path / "main_ps4.hdr").write_bytes(cipher)
+    (tmp_path / "main_ps4_0.ark").write_bytes(image)
+    for _ in range(3):  # thread scheduling must not matter
+        run(cli, tmp_path, "-unpack", "out")
+        assert (tmp_path / "out" / "ps4" / "dup.bin").read_bytes() == second
+        assert (tmp_path / "out" / "ps4" / "other.bin").read_bytes() == other
+        assert (tmp_path / "out" / "ps4" / "empty_dup.bin").read_bytes() == b""
+
+
+def test_pack_fails_loudly_on_an_unreadable_file(cli, tmp_path):
+    """BuildArk gives up on the first input it cannot open (reference CArk.cpp:799-804)."""
+    if os.geteuid() == 0:
+        pytest.skip("root can read everything")
+    hdr, _, _ = arkfixture.write_archive(str(tmp_path), n_files=20, n_parts=2, seed=23)
+    run(cli, tmp_path, "-unpack", "unpacked")
+    victim = next(e for e in hdr.entries if e.size)
+    os.chmod(tmp_path / "unpacked" / victim.name, 0)
+    assert "Failed to open file" in run(cli, tmp_path, "-packall", "-pack", "unpacked", "out", expect=1)
 
 
 def test_header_codec_roundtrip_python_side():
