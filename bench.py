@@ -466,11 +466,12 @@ def roofline_block(c: Ctx, payload: int, kernel_ms: float, workload: str, clock_
                      "imad_wide_per_clk_per_sm": lanes, "note": "HBM is the binding roofline"}
     except Exception:
         pass
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            r["traffic"] = json.load(f).get(workload)
-    except Exception:
-        pass
+    if c.world == 1:  # the committed ncu captures are of the single-GPU launch (profiles/traffic.json)
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                r["traffic"] = json.load(f).get(workload)
+        except Exception:
+            pass
     return r
 
 

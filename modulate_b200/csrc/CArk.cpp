@@ -2,6 +2,7 @@
 
 #include <dirent.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/types.h>
 #include <unistd.h>
@@ -125,10 +126,15 @@ void ListFiles(const std::string& lRoot, const std::string& lRelative, std::vect
             laFiles.push_back(lName);
     }
     closedir(lpDir);
+    // names that differ only in case cannot coexist on NTFS; on a case-sensitive file system they are
+    // ordered by their bytes so that the walk is deterministic
     auto lLess = [](const std::string& lA, const std::string& lB) {
-        return std::lexicographical_compare(lA.begin(), lA.end(), lB.begin(), lB.end(), [](char a, char b) {
-            return std::toupper((unsigned char)a) < std::toupper((unsigned char)b);
-        });
+        const auto lUpperLess = [](char a, char b) { return std::toupper((unsigned char)a) < std::toupper((unsigned char)b); };
+        if (std::lexicographical_compare(lA.begin(), lA.end(), lB.begin(), lB.end(), lUpperLess))
+            return true;
+        if (std::lexicographical_compare(lB.begin(), lB.end(), lA.begin(), lA.end(), lUpperLess))
+            return false;
+        return lA < lB;
     };
     std::sort(laFiles.begin(), laFiles.end(), lLess);
     std::sort(laDirs.begin(), laDirs.end(), lLess);
@@ -246,6 +252,43 @@ struct Slot {
     int miFillLeft = 0;
     int miDrainLeft = 0;
     bool mbUsedGpu = false;
+    uint64_t muInCapacity = 0, muOutCapacity = 0;
+};
+
+// Slots handed back by a finished pipeline, kept for the next one: page-locking memory costs more than
+// moving the data does (0.3-1 ms per MiB), and a repack runs an extract and a build back to back.  At
+// most kiMaxCached slots are kept; the cache is never destroyed (the CUDA context may be gone by the
+// time static destructors run), the OS reclaims it with the process.
+struct SlotCache {
+    std::mutex mMutex;
+    std::vector<Slot> maSlots;
+    static constexpr size_t kiMaxCached = 24;
+    static SlotCache& Get()
+    {
+        static SlotCache* lpCache = new SlotCache();
+        return *lpCache;
+    }
+    bool Take(int liDevice, uint64_t luIn, uint64_t luOut, bool lbNeedGpu, Slot& lOut)
+    {
+        std::lock_guard<std::mutex> lLock(mMutex);
+        for (size_t ii = 0; ii < maSlots.size(); ++ii) {
+            Slot& lSlot = maSlots[ii];
+            if (lSlot.muInCapacity >= luIn && lSlot.muOutCapacity >= luOut && (!lbNeedGpu || (lSlot.mpStream && lSlot.miDevice == liDevice))) {
+                lOut = lSlot;
+                maSlots.erase(maSlots.begin() + (long)ii);
+                return true;
+            }
+        }
+        return false;
+    }
+    bool Give(const Slot& lSlot)
+    {
+        std::lock_guard<std::mutex> lLock(mMutex);
+        if (maSlots.size() >= kiMaxCached)
+            return false;
+        maSlots.push_back(lSlot);
+        return true;
+    }
 };
 
 struct SlotRing {
@@ -303,16 +346,24 @@ struct SlotRing {
         maSlots.resize(std::max<size_t>(1, liWanted));
         for (size_t ii = 0; ii < maSlots.size(); ++ii) {
             Slot& lSlot = maSlots[ii];
-            lSlot.miDevice = laDevices[ii % laDevices.size()];
-            lSlot.mpHostIn = (unsigned char*)mod_host_alloc(luInBytes + 32);
-            lSlot.mpHostOut = (unsigned char*)mod_host_alloc(luOutBytes + 32);
+            const int liDevice = laDevices[ii % laDevices.size()];
+            if (SlotCache::Get().Take(liDevice, luInBytes + 32, luOutBytes + 32, lbNeedGpu, lSlot)) {
+                lSlot.meState = Slot::eFree;
+                lSlot.mbUsedGpu = false;
+                continue;
+            }
+            lSlot.miDevice = liDevice;
+            lSlot.muInCapacity = luInBytes + 32;
+            lSlot.muOutCapacity = luOutBytes + 32;
+            lSlot.mpHostIn = (unsigned char*)mod_host_alloc(lSlot.muInCapacity);
+            lSlot.mpHostOut = (unsigned char*)mod_host_alloc(lSlot.muOutCapacity);
             if (!lSlot.mpHostIn || !lSlot.mpHostOut)
                 return false;
             if (lbNeedGpu) {
                 if (mod_init(lSlot.miDevice) != MOD_OK)
                     return false;
-                lSlot.mpDevIn = mod_device_alloc(luInBytes + 32);
-                lSlot.mpDevOut = mod_device_alloc(luOutBytes + 32);
+                lSlot.mpDevIn = mod_device_alloc(lSlot.muInCapacity);
+                lSlot.mpDevOut = mod_device_alloc(lSlot.muOutCapacity);
                 lSlot.mpStream = mod_stream_create();
                 if (!lSlot.mpDevIn || !lSlot.mpDevOut || !lSlot.mpStream)
                     return false;
@@ -323,10 +374,12 @@ struct SlotRing {
     void Release()
     {
         for (Slot& lSlot : maSlots) {
-            if (lSlot.mpStream) {
+            if (lSlot.mpStream)
                 mod_stream_sync(lSlot.mpStream);
+            if (lSlot.mpHostIn && lSlot.mpHostOut && SlotCache::Get().Give(lSlot))
+                continue;
+            if (lSlot.mpStream)
                 mod_stream_destroy(lSlot.mpStream);
-            }
             mod_device_free(lSlot.mpDevIn);
             mod_device_free(lSlot.mpDevOut);
             mod_host_free(lSlot.mpHostIn);
@@ -617,13 +670,20 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
     SlotRing lRing;
     std::vector<mod_plan*> laPlans(laDevices.size(), nullptr);
     auto lCleanup = [&]() {
+        const double ldT0 = NowSeconds();
         lRing.Release();
+        const double ldT1 = NowSeconds();
         for (mod_plan* lpPlan : laPlans)
             mod_plan_destroy(lpPlan);
         if (liOriginalDevice >= 0)
             mod_init(liOriginalDevice);
+        if (TraceEnabled())
+            std::fprintf(stderr, "[mod] ExtractFiles cleanup: slots %.3f s, plans %.3f s\n", ldT1 - ldT0, NowSeconds() - ldT1);
     };
-    bool lbReady = lRing.Allocate(laDevices, 3, laGroups.size(), luMaxRange, luMaxPayload, true);
+    const double ldPlanned = NowSeconds();
+    const int liSlotsPerDevice = std::max(3, 6 / (int)laDevices.size());
+    bool lbReady = lRing.Allocate(laDevices, liSlotsPerDevice, laGroups.size(), luMaxRange, luMaxPayload, true);
+    const double ldSlots = NowSeconds();
     for (size_t dd = 0; dd < laDevices.size() && lbReady; ++dd)
         lbReady = mod_init(laDevices[dd]) == MOD_OK &&
                   mod_plan_create(laDescs.data(), laDescs.size(), luImageSize, luStaged, 0, &laPlans[dd]) == MOD_OK;
@@ -633,10 +693,13 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
         return eError_NoData;
     }
     const double ldAllocated = NowSeconds();
+    if (TraceEnabled())
+        std::fprintf(stderr, "[mod] ExtractFiles setup: table -> groups %.3f s, slots %.3f s, plans %.3f s\n", ldPlanned - ldStart,
+                     ldSlots - ldPlanned, ldAllocated - ldSlots);
 
     const int liCores = HostThreads();
-    TaskPool lReaders(std::max(1, std::min(4, liCores / 4)));
-    TaskPool lWriters(std::max(2, std::min(8, liCores / 2)));
+    TaskPool lReaders(std::max(2, std::min(8, liCores / 4)));
+    TaskPool lWriters(std::max(4, std::min(16, liCores / 2)));
     std::vector<int> laPartFds(mHeader.maParts.size(), -1);
 
     // stage 1 (reader threads): the image range of a group, in pieces
@@ -765,10 +828,11 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
     for (int liFd : laPartFds)
         if (liFd >= 0)
             close(liFd);
+    const size_t liSlotsUsed = lRing.maSlots.size();
     lCleanup();
     if (TraceEnabled())
         std::fprintf(stderr, "[mod] ExtractFiles: %zu groups on %zu GPU(s), %zu slots; setup %.3f s, pipeline %.3f s, drain %.3f s, free %.3f s\n",
-                     laGroups.size(), laDevices.size(), (size_t)std::min<size_t>(laGroups.size(), 3 * laDevices.size()),
+                     laGroups.size(), laDevices.size(), liSlotsUsed,
                      ldAllocated - ldStart, ldEnqueued - ldAllocated, ldWritten - ldEnqueued, NowSeconds() - ldWritten);
 
     eError leError = (eError)lRing.miError.load();
@@ -967,7 +1031,8 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
         if (liOriginalDevice >= 0)
             mod_init(liOriginalDevice);
     };
-    bool lbReady = lRing.Allocate(laDevices, 3, laGroups.size(), luMaxRange, lbAnyKey ? luMaxRange : 0, lbAnyKey);
+    const int liSlotsPerDevice = std::max(3, 6 / (int)laDevices.size());
+    bool lbReady = lRing.Allocate(laDevices, liSlotsPerDevice, laGroups.size(), luMaxRange, lbAnyKey ? luMaxRange : 0, lbAnyKey);
     for (size_t dd = 0; dd < laDevices.size() && lbReady && lbAnyKey; ++dd)
         lbReady = mod_init(laDevices[dd]) == MOD_OK &&
                   mod_plan_create(laDescs.data(), laDescs.size(), muBuiltImageSize, muBuiltImageSize, 0, &laPlans[dd]) == MOD_OK;
@@ -977,9 +1042,10 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
         return eError_NoData;
     }
 
+    const double ldReady = NowSeconds();
     const int liCores = HostThreads();
-    TaskPool lReaders(std::max(2, std::min(8, liCores / 2)));
-    TaskPool lWriters(std::max(1, std::min(4, liCores / 4)));
+    TaskPool lReaders(std::max(2, std::min(12, liCores / 2)));
+    TaskPool lWriters(std::max(2, std::min(12, liCores / 2)));
 
     // stage 1 (reader threads): the input files of a group, a few dozen per task (the reference's one
     // fread per file, CArk.cpp:796-811 -- thousands of small files are latency-bound on any file system)
@@ -1027,8 +1093,12 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
         }
         const unsigned char* lpBytes = (lSlot.mbUsedGpu ? lSlot.mpHostOut : lSlot.mpHostIn) + (lGroup.lo & 15u) + (luLo - lGroup.lo);
         const PartTarget& lPart = laTargets[liTarget];
-        if (!lRing.Failed() && !WriteFully(lPart.miFd, lpBytes, luHi - luLo, luLo - lPart.muImageStart))
-            lRing.Fail(eError_FailedToWriteData);
+        if (!lRing.Failed()) {
+            if (lPart.mpMap)  // pages of a mapped file are faulted in and filled by many threads at once
+                std::memcpy(lPart.mpMap + (luLo - lPart.muImageStart), lpBytes, (size_t)(luHi - luLo));
+            else if (!WriteFully(lPart.miFd, lpBytes, luHi - luLo, luLo - lPart.muImageStart))
+                lRing.Fail(eError_FailedToWriteData);
+        }
         lRing.DrainDone(lSlot);
     };
 
@@ -1081,11 +1151,14 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
                 uint64_t lo, hi;
             };
             std::vector<Piece> laPieces;
+            const uint64_t kuWritePiece = 4ull << 20;  // several writer threads share a group
             for (size_t tt = 0; tt < laTargets.size(); ++tt) {
                 const uint64_t luLo = std::max(lGroup.lo, laTargets[tt].muImageStart);
                 const uint64_t luHi = std::min(lGroup.hi, laTargets[tt].muImageStart + laTargets[tt].muSize);
-                if (laTargets[tt].miFd >= 0 && luHi > luLo)
-                    laPieces.push_back(Piece{tt, luLo, luHi});
+                if (laTargets[tt].miFd < 0)
+                    continue;
+                for (uint64_t luAt = luLo; luAt < luHi; luAt += kuWritePiece)
+                    laPieces.push_back(Piece{tt, luAt, std::min(luHi, luAt + kuWritePiece)});
             }
             if (laPieces.empty()) {  // every part this group falls in was skipped (existing output kept)
                 lRing.Set(lSlot, Slot::eFree);
@@ -1104,8 +1177,8 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
     lWriters.Finish();
     lCleanup();
     if (TraceEnabled())
-        std::fprintf(stderr, "[mod] SaveArk: streamed %zu groups (%s) in %.3f s\n", laGroups.size(),
-                     lbAnyKey ? "ciphered on the GPU" : "plain copy, no GPU", NowSeconds() - ldStart);
+        std::fprintf(stderr, "[mod] SaveArk: streamed %zu groups (%s): setup %.3f s, pipeline %.3f s\n", laGroups.size(),
+                     lbAnyKey ? "ciphered on the GPU" : "plain copy, no GPU", ldReady - ldStart, NowSeconds() - ldReady);
     return (eError)lRing.miError.load();
 }
 
@@ -1150,13 +1223,20 @@ eError CArk::SaveArk(const char* lpOutputDirectory, const char* lpHeaderFilename
         std::cout << "Writing " << lFilename.c_str() << "\n";
         MakeParentDirectories(lFilename);
         PartTarget lTarget;
-        lTarget.miFd = open(lFilename.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        lTarget.miFd = open(lFilename.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
         if (lTarget.miFd < 0) {
             std::cout << "Failed to open file for writing: " << lFilename.c_str() << "\n";
             continue;
         }
         lTarget.muImageStart = luCursor;
         lTarget.muSize = lPart.muSize;
+        // size the file up front and map it: writer threads then fill disjoint ranges concurrently (write()
+        // calls on one file serialise on its inode lock); if the mapping fails they fall back to pwrite
+        if (mbBuilt && lPart.muSize && ftruncate(lTarget.miFd, (off_t)lPart.muSize) == 0) {
+            void* lpMap = mmap(nullptr, lPart.muSize, PROT_READ | PROT_WRITE, MAP_SHARED, lTarget.miFd, 0);
+            if (lpMap != MAP_FAILED)
+                lTarget.mpMap = (unsigned char*)lpMap;
+        }
         laTargets.push_back(lTarget);
         luCursor += lPart.muSize;
     }
@@ -1175,8 +1255,11 @@ eError CArk::SaveArk(const char* lpOutputDirectory, const char* lpHeaderFilename
             if (lTarget.muSize)
                 leError = eError_FailedToWriteData;  // nothing to write the parts from
     }
-    for (const PartTarget& lTarget : laTargets)
+    for (const PartTarget& lTarget : laTargets) {
+        if (lTarget.mpMap)
+            munmap(lTarget.mpMap, lTarget.muSize);
         close(lTarget.miFd);
+    }
     SHOW_ERROR_AND_RETURN;
     return eError_NoError;
 }

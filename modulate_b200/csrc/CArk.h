@@ -62,6 +62,7 @@ private:
     bool ReadImageRange(std::vector<int>& laFds, uint64_t luOffset, uint64_t luSize, unsigned char* lpDst) const;
     struct PartTarget {
         int miFd = -1;             // part file open for writing
+        unsigned char* mpMap = nullptr;  // its mapping, when it could be mapped
         uint64_t muImageStart = 0; // first image byte it receives
         uint64_t muSize = 0;
     };

@@ -15,15 +15,18 @@ EXTS = ["dta_dta_ps4", "mogg", "png_ps4", "bin", "moggsong"]
 
 
 def make_names(n: int, seed: int = 1) -> List[str]:
+    """n distinct entry names; distinct also when compared case-insensitively (they have to coexist in
+    one NTFS directory tree, and the PS4 header order compares with _stricmp)."""
     rng = np.random.default_rng(seed)
-    names = set()
+    names = {}
     while len(names) < n:
         d = DIRS[int(rng.integers(0, len(DIRS)))]
         stem = "".join(chr(int(c)) for c in rng.integers(97, 123, size=int(rng.integers(3, 10))))
         if rng.random() < 0.2:
             stem = stem.capitalize()
-        names.add(f"{d}/{stem}.{EXTS[int(rng.integers(0, len(EXTS)))]}")
-    return sorted(names)
+        name = f"{d}/{stem}.{EXTS[int(rng.integers(0, len(EXTS)))]}"
+        names.setdefault(name.upper(), name)
+    return sorted(names.values())
 
 
 def cipher_entries(image: np.ndarray, offsets, sizes, key: int) -> None:
@@ -55,8 +58,8 @@ def reconstruct_walk(names, by_name=None):
     out = []
 
     def walk(node):
-        files = sorted([k for k in node if k[0] == "f"], key=lambda k: k[1].upper())
-        dirs = sorted([k for k in node if k[0] == "d"], key=lambda k: k[1].upper())
+        files = sorted([k for k in node if k[0] == "f"], key=lambda k: (k[1].upper(), k[1]))
+        dirs = sorted([k for k in node if k[0] == "d"], key=lambda k: (k[1].upper(), k[1]))
         for k in files:
             out.append(node[k])
         for k in dirs:
