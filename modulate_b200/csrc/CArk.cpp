@@ -119,10 +119,16 @@ void ListFiles(const std::string& lRoot, const std::string& lRelative, std::vect
         const std::string lName = lpEntry->d_name;
         if (lName == "." || lName == "..")
             continue;
-        const std::string lFull = lRoot + lRelative + lName;
-        if (IsDirectory(lFull))
+        // the directory entry usually says what it is; stat only when it does not (or for symlinks)
+        bool lbDirectory = lpEntry->d_type == DT_DIR, lbFile = lpEntry->d_type == DT_REG;
+        if (!lbDirectory && !lbFile) {
+            const std::string lFull = lRoot + lRelative + lName;
+            lbDirectory = IsDirectory(lFull);
+            lbFile = !lbDirectory && FileSize(lFull) >= 0;
+        }
+        if (lbDirectory)
             laDirs.push_back(lName);
-        else if (FileSize(lFull) >= 0)
+        else if (lbFile)
             laFiles.push_back(lName);
     }
     closedir(lpDir);
@@ -884,14 +890,15 @@ eError CArk::ConstructFromDirectory(const char* lpInputDirectory, const CArk& lR
     mHeader = modark::HeaderImage();
     mHeader.mbPS4 = CSettings::mbPS4;
     uint64_t luTotalFileSize = 0;
+    // name -> FIRST entry of that name in the reference header (the reference scans linearly for the first
+    // match of the name hash, CArk.cpp:1194-1209)
+    std::unordered_map<std::string, const modark::FileDef*> lReferenceByName;
+    lReferenceByName.reserve(lReferenceHeader.mHeader.maFiles.size());
+    for (const modark::FileDef& lCandidate : lReferenceHeader.mHeader.maFiles)
+        lReferenceByName.emplace(lCandidate.mName, &lCandidate);
     for (const std::string& lFilename : laFilenames) {
-        const modark::FileDef* lpReference = nullptr;
-        for (const modark::FileDef& lCandidate : lReferenceHeader.mHeader.maFiles) {
-            if (lCandidate.mName == lFilename) {
-                lpReference = &lCandidate;
-                break;
-            }
-        }
+        const auto lFound = lReferenceByName.find(lFilename);
+        const modark::FileDef* lpReference = lFound == lReferenceByName.end() ? nullptr : lFound->second;
         if (!lpReference && CSettings::mbIgnoreNewFiles)
             continue;  // only files the reference header knows are repacked (-pack); -pack_add lifts this
         if (!CSettings::mbPackAllFiles && !ShouldPackFile(laSongs, lFilename.c_str()))

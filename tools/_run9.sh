@@ -1,0 +1,9 @@
+nvidia-smi -L | wc -l; nproc
+for n in 8 4; do
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 20 --warmup 5 > gpurun_out/bench_n$n.log 2>&1; echo "bench n$n rc=$?"
+grep "^{" gpurun_out/bench_n$n.log | tail -1 | python -c "
+import sys,json
+d=json.loads(sys.stdin.read())
+print('N',d['n_gpus'],'value %.0f'%d['value'],'ms/step %.3f'%d['ms_per_step'],'frac %.3f'%d['roofline']['frac'],'sustained %.3f'%d['roofline']['sustained']['frac'],'parity',d['parity_bytes_checked'],'e2e %.1f'%d['e2e']['value'],'inproc',d['extra'].get('e2e_inprocess'))"
+done
+timeout 300 python tools/pcie_probe.py --gpus 8 --mib 512 --json gpurun_out/pcie_8.json; echo "probe rc=$?"
