@@ -225,6 +225,14 @@ int HostThreads()
     return luCores ? (int)luCores : 4;
 }
 
+// Tuning aid: MOD_IO_<NAME>=<n> overrides a pipeline's thread / slot count (tools/unpack_timing.py sweeps them).
+int Tunable(const char* lpName, int liDefault)
+{
+    const char* lpValue = std::getenv(lpName);
+    const int liValue = lpValue && *lpValue ? std::atoi(lpValue) : 0;
+    return liValue > 0 ? liValue : liDefault;
+}
+
 // GPUs the facade spreads an archive over: every visible device (MOD_DEVICES = bit mask restricts
 // them) once the archive is large enough to be worth it, else only the calling thread's device.
 std::vector<int> FacadeDevices(uint64_t luBytes)
@@ -642,7 +650,7 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
         uint64_t srcLo, srcHi;  // image range
         uint64_t dstLo, dstHi;  // range of the byte-packed staging space
     };
-    const uint64_t kuGroupBytes = 32ull << 20;
+    const uint64_t kuGroupBytes = (uint64_t)Tunable("MOD_IO_GROUP_MIB", 32) << 20;
     std::vector<Group> laGroups;
     std::vector<mod_desc> laDescs(laOrder.size());
     uint64_t luMaxRange = 1, luMaxPayload = 1, luStaged = 0;
@@ -687,7 +695,7 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
             std::fprintf(stderr, "[mod] ExtractFiles cleanup: slots %.3f s, plans %.3f s\n", ldT1 - ldT0, NowSeconds() - ldT1);
     };
     const double ldPlanned = NowSeconds();
-    const int liSlotsPerDevice = std::max(3, 6 / (int)laDevices.size());
+    const int liSlotsPerDevice = Tunable("MOD_IO_SLOTS", std::max(3, 6 / (int)laDevices.size()));
     bool lbReady = lRing.Allocate(laDevices, liSlotsPerDevice, laGroups.size(), luMaxRange, luMaxPayload, true);
     const double ldSlots = NowSeconds();
     for (size_t dd = 0; dd < laDevices.size() && lbReady; ++dd)
@@ -704,8 +712,8 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
                      ldSlots - ldPlanned, ldAllocated - ldSlots);
 
     const int liCores = HostThreads();
-    TaskPool lReaders(std::max(2, std::min(8, liCores / 4)));
-    TaskPool lWriters(std::max(4, std::min(16, liCores / 2)));
+    TaskPool lReaders(Tunable("MOD_IO_READERS", std::max(2, std::min(8, liCores / 4))));
+    TaskPool lWriters(Tunable("MOD_IO_WRITERS", std::max(4, std::min(16, liCores / 2))));
     std::vector<int> laPartFds(mHeader.maParts.size(), -1);
 
     // stage 1 (reader threads): the image range of a group, in pieces
@@ -1038,7 +1046,7 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
         if (liOriginalDevice >= 0)
             mod_init(liOriginalDevice);
     };
-    const int liSlotsPerDevice = std::max(3, 6 / (int)laDevices.size());
+    const int liSlotsPerDevice = Tunable("MOD_IO_SLOTS", std::max(3, 6 / (int)laDevices.size()));
     bool lbReady = lRing.Allocate(laDevices, liSlotsPerDevice, laGroups.size(), luMaxRange, lbAnyKey ? luMaxRange : 0, lbAnyKey);
     for (size_t dd = 0; dd < laDevices.size() && lbReady && lbAnyKey; ++dd)
         lbReady = mod_init(laDevices[dd]) == MOD_OK &&
@@ -1051,8 +1059,8 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
 
     const double ldReady = NowSeconds();
     const int liCores = HostThreads();
-    TaskPool lReaders(std::max(2, std::min(12, liCores / 2)));
-    TaskPool lWriters(std::max(2, std::min(12, liCores / 2)));
+    TaskPool lReaders(Tunable("MOD_IO_READERS", std::max(2, std::min(12, liCores / 2))));
+    TaskPool lWriters(Tunable("MOD_IO_WRITERS", std::max(2, std::min(12, liCores / 2))));
 
     // stage 1 (reader threads): the input files of a group, a few dozen per task (the reference's one
     // fread per file, CArk.cpp:796-811 -- thousands of small files are latency-bound on any file system)

@@ -32,6 +32,47 @@ def test_reference_arm_line():
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
 
 
+def test_device_payload_is_the_synth_stream():
+    """bench.py generates its plaintext where the buffer lives (torch int64 splitmix64); it must be the
+    same counter-based stream the oracle side regenerates window by window (tests/synth.py)."""
+    import numpy as np
+    import torch
+
+    sys.path.insert(0, ROOT)
+    import bench
+    import synth
+    for off, n in [(0, 64), (3, 1001), (123457, 1 << 18), ((1 << 34) + 5, 4099), ((16 << 30) - 77, 77)]:
+        out = torch.empty(n, dtype=torch.uint8)
+        bench.device_payload(torch, out, off, slice_bytes=1 << 16)
+        assert (out.numpy() == synth.payload(off, n)).all(), (off, n)
+
+
+def test_parity_windows_cover_both_sides_of_every_cut():
+    """Every rank checks the first and last 256 KiB of each piece of its shard, so both sides of every
+    interior cut and part boundary are compared by one rank or the other, and at least 64 MiB per rank."""
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import bench
+    import modulate_b200 as mb
+    descs = bench.global_descs(mb, "cfg3")
+    for world in (1, 2, 3, 8):
+        covered_starts, covered_ends = set(), set()
+        for rank in range(world):
+            shard = mb.shard_descs(descs, rank, world) if world > 1 else descs
+            wins = bench.parity_windows(shard, bench.PARITY_TARGET, np.random.default_rng(rank))
+            assert sum(w[2] for w in wins) >= bench.PARITY_TARGET
+            for i, pos, n in wins:
+                assert 0 <= pos and pos + n <= int(shard[i]["len"])
+                if pos == 0:
+                    covered_starts.add(int(shard[i]["dst_off"]))
+                if pos + n == int(shard[i]["len"]):
+                    covered_ends.add(int(shard[i]["dst_off"]) + int(shard[i]["len"]))
+        total = int(descs["len"].sum())
+        cuts = {total * r // world & ~15 for r in range(1, world)} | {int(d["dst_off"]) for d in descs[1:]}
+        assert cuts <= covered_starts and cuts <= covered_ends
+
+
 @pytest.mark.gpu
 def test_gpu_arm_line():
     """The headline line: BASELINE configs[2] (16 GiB multi-part set), parity checked in the run."""
