@@ -642,7 +642,7 @@ def measure_cfg5(c: Ctx, total: int = GIB, n_files: int = 10_000) -> dict:
     import oracle
     from oracle import ark_oracle as ao
     from oracle import dta_oracle as do
-    from test_dta_codec import song_config_tree
+    from arkfixture import song_config_tree
 
     mb = c.mb
     base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()

@@ -242,10 +242,10 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
         }
     }
 
-    uint32_t s[U], v0[U];
+    uint32_t s[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
-        v0[u] = s[u] = mulmod(st, pw[u]);  // state just before this thread's chunk of round u
+        s[u] = mulmod(st, pw[u]);  // state just before this thread's chunk of round u
 
     // A lazily reduced state t = hi + lo31 (hi <= 16807) is already canonical unless bit 31 is set,
     // which needs lo31 >= 2^31 - 16807: about 2^-17 per byte.  So the low bytes are packed straight
@@ -311,7 +311,7 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
         }
         uint4 out = make_uint4(data.x ^ ks[u][0], data.y ^ ks[u][1], data.z ^ ks[u][2], data.w ^ ks[u][3]);
         if (__builtin_expect(redo, 0))  // some state of the group needed a canonical subtract: redo exactly
-            out = cycle_chunk_exact(data, v0[u], two);
+            out = cycle_chunk_exact(data, mulmod(st, __ldg(&g_chunk_pow[idx])), two);  // (start state recomputed: rare path)
         if (idx - f_lo < f_hi - f_lo)
             stg128(dp + 16ull * T * u, out);
         else if (idx < n_valid)

@@ -175,3 +175,16 @@ def fixture_file_bytes(f) -> bytes:
     if f.get("content") == "amp_songs_config":
         return song_config_blobs()[1]
     return synth.payload(f["seed"], f["size"]).tobytes()
+
+
+def song_config_tree():
+    """A small amp_config-like DTA script: (key value) pairs inside nested trees (dta_oracle tuple form)."""
+    import struct
+
+    def sym(s):
+        return ("str", 5, s.encode())
+    song = ("tree", 16, 12, [sym("song"), ("tree", 16, 13, [sym("name"), ("str", 18, b"Perfect Brain")]),
+                             ("tree", 16, 14, [sym("bpm"), ("int", 0, 120)]),
+                             ("tree", 16, 15, [sym("preview_start_ms"), ("int", 6, 30000)]),
+                             ("tree", 17, 16, [sym("boss_level"), ("int", 0, -1), ("float", 1, struct.pack("<f", 0.5))])])
+    return ("tree", 16, 1, [sym("songs"), song, ("tree", 16, 20, [sym("unlock_tokens"), ("int", 0, 3)])])

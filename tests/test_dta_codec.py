@@ -30,15 +30,7 @@ def random_tree(rng, depth=0, ttype=16):
     return ("tree", ttype, int(rng.integers(0, 3000)), children)
 
 
-def song_config_tree():
-    """A small amp_config-like script: (key value) pairs inside nested trees."""
-    def sym(s):
-        return ("str", 5, s.encode())
-    song = ("tree", 16, 12, [sym("song"), ("tree", 16, 13, [sym("name"), ("str", 18, b"Perfect Brain")]),
-                             ("tree", 16, 14, [sym("bpm"), ("int", 0, 120)]),
-                             ("tree", 16, 15, [sym("preview_start_ms"), ("int", 6, 30000)]),
-                             ("tree", 17, 16, [sym("boss_level"), ("int", 0, -1), ("float", 1, struct.pack("<f", 0.5))])])
-    return ("tree", 16, 1, [sym("songs"), song, ("tree", 16, 20, [sym("unlock_tokens"), ("int", 0, 3)])])
+from arkfixture import song_config_tree  # noqa: E402,F401  (shared with bench.py's cfg5 workload)
 
 
 def test_oracle_roundtrip_and_known_bytes():

@@ -65,7 +65,7 @@ def test_repack_on_gpu_end_to_end(tmp_path, ps4):
     run(tmp_path, *pre, "-bodykey", str(key), "-unpack", "unpacked")
     # the host-side patch: one entry is a binary DTA script; change a value in it with the DTB codec
     from oracle import dta_oracle as do
-    from test_dta_codec import song_config_tree
+    from arkfixture import song_config_tree
     victim = next(e for e in hdr.entries if e.size > 100)
     tree = song_config_tree()
     open(tmp_path / "unpacked" / victim.name, "wb").write(do.serialise([tree]))
