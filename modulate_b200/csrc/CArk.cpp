@@ -640,33 +640,57 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
         }
     }
 
-    // order by where the entries sit in the image; groups of consecutive entries (~32 MiB of payload each)
+    // order by where the entries sit in the image, cut entries larger than a group into PIECES (a piece that
+    // starts p bytes into its entry continues the entry's keystream from the jumped key), then form groups of
+    // consecutive pieces (~32 MiB of payload each): a slot never has to hold more than about one group
     std::vector<uint32_t> laOrder = laWinners;
     std::stable_sort(laOrder.begin(), laOrder.end(), [&](uint32_t a, uint32_t b) {
         return mHeader.maFiles[a].mi64Offset < mHeader.maFiles[b].mi64Offset;
     });
+    struct Piece {
+        uint32_t file;        // index into mHeader.maFiles
+        uint64_t fileOffset;  // where in the output file the piece goes
+        uint32_t size;
+        bool whole;           // the piece is the whole file
+    };
     struct Group {
-        size_t first, last;     // positions in laOrder
+        size_t first, last;     // positions in laPieces
         uint64_t srcLo, srcHi;  // image range
         uint64_t dstLo, dstHi;  // range of the byte-packed staging space
     };
     const uint64_t kuGroupBytes = (uint64_t)Tunable("MOD_IO_GROUP_MIB", 32) << 20;
+    std::vector<Piece> laPieces;
+    laPieces.reserve(laOrder.size());
+    for (uint32_t luFile : laOrder) {
+        const uint64_t luSize = (uint64_t)mHeader.maFiles[luFile].miSize;
+        if (luSize <= kuGroupBytes + kuGroupBytes / 2) {
+            laPieces.push_back(Piece{luFile, 0, (uint32_t)luSize, true});
+            continue;
+        }
+        for (uint64_t luAt = 0; luAt < luSize;) {
+            uint64_t luTake = std::min(kuGroupBytes, luSize - luAt);
+            if (luSize - luAt - luTake < kuGroupBytes / 2)
+                luTake = luSize - luAt;  // no short tail piece
+            laPieces.push_back(Piece{luFile, luAt, (uint32_t)luTake, false});
+            luAt += luTake;
+        }
+    }
     std::vector<Group> laGroups;
-    std::vector<mod_desc> laDescs(laOrder.size());
+    std::vector<mod_desc> laDescs(laPieces.size());
     uint64_t luMaxRange = 1, luMaxPayload = 1, luStaged = 0;
-    bool lbAnyKey = false;
-    for (size_t liFirst = 0; liFirst < laOrder.size();) {
+    for (size_t liFirst = 0; liFirst < laPieces.size();) {
         Group lGroup{liFirst, liFirst, UINT64_MAX, 0, luStaged, luStaged};
-        while (lGroup.last < laOrder.size() && (lGroup.dstHi - lGroup.dstLo < kuGroupBytes || lGroup.last == liFirst)) {
-            const modark::FileDef& lFile = mHeader.maFiles[laOrder[lGroup.last]];
-            if (lFile.miSize) {
-                lGroup.srcLo = std::min(lGroup.srcLo, (uint64_t)lFile.mi64Offset);
-                lGroup.srcHi = std::max(lGroup.srcHi, (uint64_t)lFile.mi64Offset + (uint64_t)lFile.miSize);
+        while (lGroup.last < laPieces.size() && (lGroup.dstHi - lGroup.dstLo < kuGroupBytes || lGroup.last == liFirst)) {
+            const Piece& lPiece = laPieces[lGroup.last];
+            const uint64_t luSource = (uint64_t)mHeader.maFiles[lPiece.file].mi64Offset + lPiece.fileOffset;
+            if (lPiece.size) {
+                lGroup.srcLo = std::min(lGroup.srcLo, luSource);
+                lGroup.srcHi = std::max(lGroup.srcHi, luSource + lPiece.size);
             }
-            const int liKey = EntryKey(laOrder[lGroup.last]);
-            lbAnyKey = lbAnyKey || (liKey % 0x7FFFFFFF) != 0;
-            laDescs[lGroup.last] = mod_desc{(uint64_t)lFile.mi64Offset, lGroup.dstHi, (uint32_t)lFile.miSize, liKey};
-            lGroup.dstHi += (uint64_t)lFile.miSize;
+            const int liKey = EntryKey(lPiece.file);
+            laDescs[lGroup.last] = mod_desc{luSource, lGroup.dstHi, lPiece.size,
+                                            lPiece.fileOffset ? mod_key_jump(liKey, lPiece.fileOffset) : liKey};
+            lGroup.dstHi += lPiece.size;
             ++lGroup.last;
         }
         if (lGroup.srcLo == UINT64_MAX)
@@ -676,6 +700,33 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
         luMaxPayload = std::max(luMaxPayload, lGroup.dstHi - lGroup.dstLo);
         laGroups.push_back(lGroup);
         liFirst = lGroup.last;
+    }
+
+    // files that arrive in several pieces are created (and emptied) up front, so that the pieces -- written by
+    // whichever threads get them, in any order -- only ever pwrite into an existing file
+    std::vector<uint8_t> laSkipFile(liCount, 0);
+    for (const Piece& lPiece : laPieces) {
+        if (lPiece.whole || lPiece.fileOffset != 0)
+            continue;
+        const modark::FileDef& lFile = mHeader.maFiles[lPiece.file];
+        const std::string lOutputPath = lTarget + lFile.mName;
+        laSkipFile[lPiece.file] = 1;
+        if (EscapesTarget(lFile.mName)) {
+            std::cout << "Refusing to write outside the target directory: " << lFile.mName.c_str() << "\n";
+        } else if (KeepExistingOutput(lOutputPath)) {
+            VERBOSE_OUT("Output file already exists, skipping: " << lOutputPath.c_str() << "\n");
+        } else if (!MakeParentDirectories(lOutputPath)) {
+            eError leError = eError_FailedToCreateDirectory;
+            SHOW_ERROR_AND_RETURN;
+        } else {
+            const int liFd = open(lOutputPath.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+            if (liFd < 0) {
+                std::cout << "Failed to create " << lOutputPath.c_str() << "\n";
+            } else {
+                close(liFd);
+                laSkipFile[lPiece.file] = 0;
+            }
+        }
     }
 
     // slots on every GPU in use, and the archive's plan on each of them
@@ -750,8 +801,21 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
             lRing.Fail(eError_InvalidData);
         }
         for (size_t ii = liFrom; ii < liTo && !lRing.Failed(); ++ii) {
-            const modark::FileDef& lFile = mHeader.maFiles[laOrder[ii]];
+            const Piece& lPiece = laPieces[ii];
+            const modark::FileDef& lFile = mHeader.maFiles[lPiece.file];
             const std::string lOutputPath = lTarget + lFile.mName;
+            const unsigned char* lpBytes = lSlot.mpHostOut + (lGroup.dstLo & 15u) + (laDescs[ii].dst_off - lGroup.dstLo);
+            if (!lPiece.whole) {  // one piece of a big file that was created up front
+                if (laSkipFile[lPiece.file])
+                    continue;
+                const int liFd = open(lOutputPath.c_str(), O_WRONLY);
+                const bool lbOk = liFd >= 0 && WriteFully(liFd, lpBytes, lPiece.size, lPiece.fileOffset);
+                if (liFd >= 0)
+                    close(liFd);
+                if (!lbOk)
+                    lRing.Fail(eError_FailedToWriteData);
+                continue;
+            }
             if (EscapesTarget(lFile.mName)) {
                 std::cout << "Refusing to write outside the target directory: " << lFile.mName.c_str() << "\n";
                 continue;
@@ -769,7 +833,6 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
                 std::cout << "Failed to create " << lOutputPath.c_str() << "\n";  // the reference carries on too (CArk.cpp:488-491)
                 continue;
             }
-            const unsigned char* lpBytes = lSlot.mpHostOut + (lGroup.dstLo & 15u) + (laDescs[ii].dst_off - lGroup.dstLo);
             const bool lbOk = lFile.miSize == 0 || WriteFully(liFd, lpBytes, (uint64_t)lFile.miSize, 0);
             close(liFd);
             if (!lbOk)

@@ -72,7 +72,18 @@ constexpr int kTw1Size = (int)(((1ull << 32) / kTileBytes) / kTw0Size + 2);
 __constant__ uint32_t c_tw0[kTw0Size];  // a^(kTileBytes * j)
 __constant__ uint32_t c_tw1[kTw1Size];  // a^(kTileBytes * 1024 * j)
 __constant__ uint32_t c_ainv[16];       // a^(-h): rewinds the stream to the chunk grid origin
-__device__ uint32_t g_chunk_pow[kChunksPerTile];  // a^(16 * j): thread-divergent index, so L1 rather than the constant bank
+__device__ uint32_t g_chunk_pow2[kChunksPerTile];  // 2 * a^(16 * j), PRE-DOUBLED for the multiply (see jump_lazy); the index
+                                                   // is thread-divergent, so the table lives in L1 rather than the constant bank
+
+// st * a^(16 j) for a canonical st and y2 = 2 * a^(16 j) from g_chunk_pow2, LAZILY reduced: one IMAD.WIDE and one
+// add, no canonical fold.  The result can be anything below 2^32; that is fine for the first step of a chain
+// (step_lazy is exact for every 32-bit input: the product of s and 2a is even, so hi + (lo >> 1) == s*a mod m)
+// and no output byte is ever taken from it.
+__device__ __forceinline__ uint32_t jump_lazy(uint32_t st, uint32_t y2)
+{
+    const uint64_t p = (uint64_t)st * (uint64_t)y2;
+    return (uint32_t)(p >> 32) + ((uint32_t)p >> 1);
+}
 
 // ---- 128-bit global accesses (explicit state space: the addresses are rebuilt from integers) ------
 
@@ -220,7 +231,9 @@ __device__ __noinline__ void slow_chunk(uint64_t src_byte0, uint64_t dst_chunk, 
 // kStaged: the tile's source span has been requested into shared memory by one bulk-async copy
 // (issued by thread 0 in run_tile); the granules are read from there AFTER the keystream has been
 // generated, so no register holds a load in flight.
-template <int kWs, int U, bool kStaged>
+// kFull: the tile is a whole 512 chunks and none of them is partial (every tile of a big entry but its first
+// and last): no per-chunk predicates on loads or stores at all.
+template <int kWs, int U, bool kStaged, bool kFull = false>
 __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint64_t dst_tile, const uint32_t st,
                                              const uint32_t n_valid, const uint32_t head, const uint32_t tail,
                                              const uint32_t bs, const uint32_t idx0, const uint32_t (&pw)[U],
@@ -234,7 +247,7 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
         for (int u = 0; u < U; ++u) {
             own[u] = make_uint4(0u, 0u, 0u, 0u);
             nxt[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (idx0 + (uint32_t)u * T < n_valid) {
+            if (kFull || idx0 + (uint32_t)u * T < n_valid) {
                 own[u] = ldg128(sp + 16ull * T * u);
                 if (kWs >= 0)
                     nxt[u] = ldg128(sp + 16ull * T * u + 16ull);
@@ -245,7 +258,7 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
     uint32_t s[U];
 #pragma unroll
     for (int u = 0; u < U; ++u)
-        s[u] = mulmod(st, pw[u]);  // state just before this thread's chunk of round u
+        s[u] = jump_lazy(st, pw[u]);  // state just before this thread's chunk of round u
 
     // A lazily reduced state t = hi + lo31 (hi <= 16807) is already canonical unless bit 31 is set,
     // which needs lo31 >= 2^31 - 16807: about 2^-17 per byte.  So the low bytes are packed straight
@@ -285,7 +298,7 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
         for (int u = 0; u < U; ++u) {
             own[u] = make_uint4(0u, 0u, 0u, 0u);
             nxt[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (idx0 + (uint32_t)u * T < n_valid) {
+            if (kFull || idx0 + (uint32_t)u * T < n_valid) {
                 own[u] = lds128(stage + 16u * (idx0 + (uint32_t)u * T));
                 if (kWs >= 0)
                     nxt[u] = lds128(stage + 16u * (idx0 + (uint32_t)u * T) + 16u);
@@ -297,9 +310,7 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
     const uint32_t f_lo = head ? 1u : 0u;
     const uint32_t f_hi = max(n_valid - (tail < 16u ? 1u : 0u), f_lo);
     const uint64_t dp = dst_tile + 16ull * idx0;
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const uint32_t idx = idx0 + (uint32_t)u * T;
+    auto source = [&](const int u) {  // the 16 source bytes that pair with chunk u, re-aligned
         uint4 data = own[u];
         if (kWs >= 0) {
             const uint32_t w[8] = {own[u].x, own[u].y, own[u].z, own[u].w, nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
@@ -309,13 +320,38 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
             data.z = __funnelshift_r(w[k + 2], w[k + 3], bs);
             data.w = __funnelshift_r(w[k + 3], w[k + 4], bs);
         }
-        uint4 out = make_uint4(data.x ^ ks[u][0], data.y ^ ks[u][1], data.z ^ ks[u][2], data.w ^ ks[u][3]);
-        if (__builtin_expect(redo, 0))  // some state of the group needed a canonical subtract: redo exactly
-            out = cycle_chunk_exact(data, mulmod(st, __ldg(&g_chunk_pow[idx])), two);  // (start state recomputed: rare path)
-        if (idx - f_lo < f_hi - f_lo)
+        return data;
+    };
+    auto emit = [&](const int u, const uint4& out) {
+        const uint32_t idx = idx0 + (uint32_t)u * T;
+        if (kFull || idx - f_lo < f_hi - f_lo)
             stg128(dp + 16ull * T * u, out);
         else if (idx < n_valid)
             store_partial(dp + 16ull * T * u, out, idx == 0u ? head : 0u, idx + 1u == n_valid ? tail : 16u);
+    };
+    if (__builtin_expect(redo, 0)) {
+        // some state of this thread's chunks needed a canonical subtract (~1 thread in 2 000): redo all four
+        // exactly, from start states recomputed here (nothing is kept live for this path)
+#pragma unroll 1
+        for (int u = 0; u < U; ++u) {
+            const uint32_t idx = idx0 + (uint32_t)u * T;
+            uint4 data = own[0];
+#pragma unroll
+            for (int v = 0; v < U; ++v)
+                if (v == u)
+                    data = source(v);
+            const uint4 out = cycle_chunk_exact(data, jump_lazy(st, __ldg(&g_chunk_pow2[idx])), two);
+#pragma unroll
+            for (int v = 0; v < U; ++v)
+                if (v == u)
+                    emit(v, out);
+        }
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint4 data = source(u);
+        emit(u, make_uint4(data.x ^ ks[u][0], data.y ^ ks[u][1], data.z ^ ks[u][2], data.w ^ ks[u][3]));
     }
 }
 
@@ -332,6 +368,12 @@ __device__ __forceinline__ void run_tile(const BatchArgs& a, const int64_t src_r
     const uint64_t sv = (uint64_t)a.src + (uint64_t)src_rel;  // source address that pairs with chunk 0, byte 0
     const uint32_t shift = (uint32_t)sv & 15u;
     const uint64_t src_tile = sv - shift;
+    constexpr uint32_t kFullGeom = (uint32_t)kChunksPerTile | (16u << 16);  // pack_geom(kChunksPerTile, 0, 16)
+    if (!kGeneral && geom == kFullGeom && shift == 0u && src_tile >= a.src_lo16 && src_tile + kTileBytes <= a.src_hi16) {
+        // CTA-uniform fast exit of the co-aligned flavour: an interior tile of a big entry, nothing to decode
+        process_tile<-1, U, false, true>(src_tile, dst_tile, st, (uint32_t)kChunksPerTile, 0u, 16u, 0u, idx0, pw, a.two, stage, bar);
+        return;
+    }
     const uint32_t n_valid = geom & 0xFFFu, head = (geom >> 12) & 15u, tail = (geom >> 16) & 31u;
 
     // whole-granule loads are allowed only inside the source buffer (CTA-uniform test); a misaligned
@@ -343,14 +385,14 @@ __device__ __forceinline__ void run_tile(const BatchArgs& a, const int64_t src_r
             const uint32_t idx = idx0 + (uint32_t)u * (uint32_t)kThreadsPerCta;
             if (idx < n_valid)
                 slow_chunk(sv + 16ull * idx, dst_tile + 16ull * idx, idx == 0u ? head : 0u,
-                           idx + 1u == n_valid ? tail : 16u, mulmod(st, g_chunk_pow[idx]), a.two);
+                           idx + 1u == n_valid ? tail : 16u, jump_lazy(st, g_chunk_pow2[idx]), a.two);
         }
         return;
     }
 
     const uint32_t bs = (shift & 3u) * 8u;
     if (!kGeneral) {
-        process_tile<-1, U, false>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar);
+        process_tile<-1, U, false, false>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar);
         return;
     }
     constexpr bool kStaged = MODK_STAGE != 0;
@@ -427,7 +469,7 @@ __device__ __forceinline__ void load_chunk_pows(uint32_t (&pw)[U], uint32_t idx0
 {
 #pragma unroll
     for (int u = 0; u < U; ++u)
-        pw[u] = __ldg(&g_chunk_pow[idx0 + (uint32_t)u * (uint32_t)kThreadsPerCta]);
+        pw[u] = __ldg(&g_chunk_pow2[idx0 + (uint32_t)u * (uint32_t)kThreadsPerCta]);
 }
 
 // Batched kernel: CTA b owns tile b (one 32-byte record, broadcast to the CTA) and retires.  A CTA
@@ -514,7 +556,7 @@ cudaError_t upload_tables()
         for (int h = 0; h < 16; ++h)
             h_ainv[h] = modlcg::pow_a_inv((uint64_t)h);
         for (int j = 0; j < kChunksPerTile; ++j)
-            h_chunk[j] = modlcg::pow_a(16ull * (uint64_t)j);
+            h_chunk[j] = 2u * modlcg::pow_a(16ull * (uint64_t)j);
         return true;
     }();  // thread-safe: several device workers may call this at once
     (void)built;
@@ -522,7 +564,7 @@ cudaError_t upload_tables()
     if ((err = cudaMemcpyToSymbol(c_tw0, h_tw0, sizeof(h_tw0))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_tw1, h_tw1, sizeof(h_tw1))) != cudaSuccess) return err;
     if ((err = cudaMemcpyToSymbol(c_ainv, h_ainv, sizeof(h_ainv))) != cudaSuccess) return err;
-    if ((err = cudaMemcpyToSymbol(g_chunk_pow, h_chunk, sizeof(h_chunk))) != cudaSuccess) return err;
+    if ((err = cudaMemcpyToSymbol(g_chunk_pow2, h_chunk, sizeof(h_chunk))) != cudaSuccess) return err;
     return cudaSuccess;
 }
 
