@@ -1064,8 +1064,15 @@ eError CArk::BuildArk(const char* lpInputDirectory, std::vector<SSongConfig> laS
 eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
 {
     const double ldStart = NowSeconds();
-    // non-empty entries in table order == image order
-    std::vector<uint32_t> laOrder;
+    // non-empty entries in table order == image order; files larger than a group are read (and ciphered) in
+    // PIECES, each continuing the entry's keystream from the jumped key, so a slot stays about one group big
+    struct Piece {
+        uint32_t file;        // index into mHeader.maFiles
+        uint64_t fileOffset;  // where in the input file the piece starts
+        uint32_t size;
+    };
+    const uint64_t kuGroupBytes = (uint64_t)Tunable("MOD_IO_GROUP_MIB", 32) << 20;
+    std::vector<Piece> laPieces;
     std::vector<mod_desc> laDescs;
     bool lbAnyKey = false;
     for (size_t ii = 0; ii < mHeader.maFiles.size(); ++ii) {
@@ -1074,22 +1081,29 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
             continue;
         const int liKey = EntryKey(ii);
         lbAnyKey = lbAnyKey || (liKey % 0x7FFFFFFF) != 0;
-        laOrder.push_back((uint32_t)ii);
-        laDescs.push_back(mod_desc{(uint64_t)lFile.mi64Offset, (uint64_t)lFile.mi64Offset, (uint32_t)lFile.miSize, liKey});
+        const uint64_t luSize = (uint64_t)lFile.miSize;
+        for (uint64_t luAt = 0; luAt < luSize;) {
+            uint64_t luTake = luSize <= kuGroupBytes + kuGroupBytes / 2 ? luSize : std::min(kuGroupBytes, luSize - luAt);
+            if (luSize - luAt - luTake < kuGroupBytes / 2)
+                luTake = luSize - luAt;  // no short tail piece
+            const uint64_t luImage = (uint64_t)lFile.mi64Offset + luAt;
+            laPieces.push_back(Piece{(uint32_t)ii, luAt, (uint32_t)luTake});
+            laDescs.push_back(mod_desc{luImage, luImage, (uint32_t)luTake, luAt ? mod_key_jump(liKey, luAt) : liKey});
+            luAt += luTake;
+        }
     }
-    if (laOrder.empty())
+    if (laPieces.empty())
         return eError_NoError;
 
     struct Group {
-        size_t first, last;  // positions in laOrder
+        size_t first, last;  // positions in laPieces
         uint64_t lo, hi;     // image range
     };
-    const uint64_t kuGroupBytes = 32ull << 20;
     std::vector<Group> laGroups;
     uint64_t luMaxRange = 1;
-    for (size_t liFirst = 0; liFirst < laOrder.size();) {
+    for (size_t liFirst = 0; liFirst < laPieces.size();) {
         Group lGroup{liFirst, liFirst, laDescs[liFirst].src_off, laDescs[liFirst].src_off};
-        while (lGroup.last < laOrder.size() && (lGroup.hi - lGroup.lo < kuGroupBytes || lGroup.last == liFirst)) {
+        while (lGroup.last < laPieces.size() && (lGroup.hi - lGroup.lo < kuGroupBytes || lGroup.last == liFirst)) {
             lGroup.hi = laDescs[lGroup.last].src_off + laDescs[lGroup.last].len;
             ++lGroup.last;
         }
@@ -1131,14 +1145,15 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
         const Group& lGroup = laGroups[gg];
         Slot& lSlot = lRing.maSlots[gg % lRing.maSlots.size()];
         for (size_t ii = liFrom; ii < liTo && !lRing.Failed(); ++ii) {
-            const modark::FileDef& lFile = mHeader.maFiles[laOrder[ii]];
+            const Piece& lPiece = laPieces[ii];
+            const modark::FileDef& lFile = mHeader.maFiles[lPiece.file];
             const int liFd = open((mBuildInputDirectory + lFile.mName).c_str(), O_RDONLY);
             if (liFd < 0) {
                 lRing.Fail(eError_FailedToOpenFile);
                 break;
             }
-            unsigned char* lpDst = lSlot.mpHostIn + (lGroup.lo & 15u) + ((uint64_t)lFile.mi64Offset - lGroup.lo);
-            const bool lbOk = ReadFully(liFd, lpDst, (uint64_t)lFile.miSize, 0);  // a file that shrank reads as zeros
+            unsigned char* lpDst = lSlot.mpHostIn + (lGroup.lo & 15u) + (laDescs[ii].src_off - lGroup.lo);
+            const bool lbOk = ReadFully(liFd, lpDst, lPiece.size, lPiece.fileOffset);  // a file that shrank reads as zeros
             close(liFd);
             if (!lbOk)
                 lRing.Fail(eError_FailedToOpenFile);

@@ -58,6 +58,9 @@ using modlcg::low8_canonical;
 #define MODK_STAGE 1             // general kernels: 1 = the tile's source span is staged through shared memory by ONE
                                  // bulk-async copy per CTA (cp.async.bulk + mbarrier), 0 = two LDG.128 per chunk into registers
 #endif
+#ifndef MODK_GENERAL_FULL
+#define MODK_GENERAL_FULL 1      // general kernels: separate predicate-free code for interior tiles (doubles their code size)
+#endif
 #ifndef MODK_HOIST_POW
 #define MODK_HOIST_POW 1         // batched kernel: request the jump factors before the tile record arrives
 #endif
@@ -401,6 +404,18 @@ __device__ __forceinline__ void run_tile(const BatchArgs& a, const int64_t src_r
         const uint32_t bytes = 16u * (n_valid + (shift ? 1u : 0u));
         mbar_expect_tx(bar, bytes);
         bulk_g2s(stage, src_tile, bytes, bar);
+    }
+#endif
+#if MODK_GENERAL_FULL
+    if (geom == kFullGeom) {  // CTA-uniform: an interior tile of a big entry -- no per-chunk predicates
+        switch (shift ? (int)(shift >> 2) : -1) {
+        case -1: process_tile<-1, U, kStaged, true>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar); break;
+        case 0: process_tile<0, U, kStaged, true>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar); break;
+        case 1: process_tile<1, U, kStaged, true>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar); break;
+        case 2: process_tile<2, U, kStaged, true>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar); break;
+        default: process_tile<3, U, kStaged, true>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar); break;
+        }
+        return;
     }
 #endif
     if (shift == 0u) {
