@@ -184,6 +184,32 @@ def test_unpack_duplicate_names_resolve_in_table_order(cli, tmp_path):
         assert (tmp_path / "out" / "ps4" / "empty_dup.bin").read_bytes() == b""
 
 
+def test_large_entries_travel_in_pieces(cli, tmp_path, monkeypatch):
+    """Entries larger than a pipeline group are cut into pieces (jumped keys) so that a slot never has to hold
+    a whole big file: same files out of -unpack, same archive out of -pack_add.  MOD_IO_GROUP_MIB=1 makes a
+    few-MiB entry 'large'."""
+    import subprocess
+    key = 0x2468ACE
+    sizes = [3_500_000, 10, 0, 2_200_001, 70_000, 1_572_864, 5] + [30_000] * 20
+    hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), n_files=len(sizes), n_parts=2, seed=29, body_key=key, sizes=sizes)
+    env = dict(os.environ, MOD_IO_GROUP_MIB="1")
+
+    def run_env(*args):
+        out = subprocess.run([cli, *args], cwd=tmp_path, capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0, out.stdout + out.stderr
+
+    run_env("-bodykey", str(key), "-unpack", "out")
+    check_unpacked(tmp_path / "out", hdr, payloads)
+    run_env("-bodykey", str(key), "-packall", "-pack_add", "out", "re")
+    run(cli, tmp_path / "re", "-bodykey", str(key), "-unpack", "again")       # default group size reads it back
+    check_unpacked(tmp_path / "re" / "again", hdr, payloads)
+    new, _ = arkfixture.read_header(str(tmp_path / "re" / "main_ps4.hdr"))
+    image = np.frombuffer(b"".join(open(tmp_path / "re" / p, "rb").read() for p, _ in new.parts), np.uint8)
+    by_name = {e.name: p for e, p in zip(hdr.entries, payloads)}
+    for e in new.entries:  # every entry, big ones included, is one continuous keystream from its first byte
+        assert oracle.cycle(image[e.offset:e.offset + e.size], key).tobytes() == by_name[e.name], e.name
+
+
 def test_pack_fails_loudly_on_an_unreadable_file(cli, tmp_path):
     """BuildArk gives up on the first input it cannot open (reference CArk.cpp:799-804)."""
     if os.geteuid() == 0:

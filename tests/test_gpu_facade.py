@@ -112,3 +112,20 @@ def test_unpack_large_archive_uses_every_gpu(tmp_path, mb):
     hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), n_files=600, n_parts=2, seed=43, body_key=key, sizes=sizes)
     mb.ark_unpack(str(tmp_path / "main_ps4.hdr"), str(tmp_path), str(tmp_path / "out"), key)
     check_unpacked(tmp_path / "out", hdr, payloads)
+
+
+def test_large_entries_travel_in_pieces_on_gpu(tmp_path, mb, monkeypatch):
+    """Entries larger than a pipeline group are cut into jumped-key pieces in both file pipelines
+    (MOD_IO_GROUP_MIB=1 makes a few-MiB entry 'large'); the bytes must not change."""
+    monkeypatch.setenv("MOD_IO_GROUP_MIB", "1")
+    key = 0x2468ACE
+    sizes = [3_500_000, 10, 0, 2_200_001, 70_000, 1_572_864, 5] + [30_000] * 20
+    hdr, payloads, _ = arkfixture.write_archive(str(tmp_path), n_files=len(sizes), n_parts=2, seed=29, body_key=key, sizes=sizes)
+    mb.ark_unpack(str(tmp_path / "main_ps4.hdr"), str(tmp_path), str(tmp_path / "out"), key)
+    check_unpacked(tmp_path / "out", hdr, payloads)
+    os.makedirs(tmp_path / "re")
+    mb.ark_pack(str(tmp_path / "main_ps4.hdr"), str(tmp_path / "out"), str(tmp_path / "re"), "main_ps4.hdr",
+                pack_all=True, ignore_new_files=False, body_key=key)
+    monkeypatch.delenv("MOD_IO_GROUP_MIB")
+    mb.ark_unpack(str(tmp_path / "re" / "main_ps4.hdr"), str(tmp_path / "re"), str(tmp_path / "again"), key)
+    check_unpacked(tmp_path / "again", hdr, payloads)
