@@ -22,6 +22,7 @@ def demangle(name):
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 res = subprocess.run(["cuobjdump", "-res-usage", so], capture_output=True, text=True).stdout
 print(f"# SASS summary of {os.path.relpath(so, ROOT)} (cuobjdump -sass / -res-usage)")
+print("# nvcc 12.9 -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo; regenerate with tools/sass_summary.py")
 print("arch:", ", ".join(sorted(set(re.findall(r"arch = (sm_\w+)", sass)))), "\n")
 print("## resources (registers / stack = spill / static shared memory)")
 for m in re.finditer(r"Function (\S+):\n\s*(.*)", res):
@@ -45,3 +46,16 @@ for f in re.split(r"\n\s*Function : ", sass)[1:]:
             shown.append(f"{k} {n}")
     print("  " + ", ".join(shown))
     print("  local-memory (spill) instructions:", sum(v for o, v in ops.items() if o.startswith(("STL", "LDL"))), "\n")
+
+print("""Reading: the hot loop is IMAD.WIDE.U32 (x 2a) + LEA.HI (Mersenne fold) per byte, three PRMT per four bytes (the
+first-level PRMT 0x7340 also gathers the states' top bytes), one three-input LOP3 for the hazard OR and one for the XOR;
+128-bit global loads / stores.  Every batched / inline kernel holds TWO copies of that loop: the predicate-free one for
+interior tiles of big entries (4 x LDG.E.128 / LDS.128, 4 x STG.E.128, no per-chunk branches; ~280 instructions per
+thread for 64 bytes = 4.4 per byte, ncu: 2.38e9 warp instructions for 16 GiB) and the predicated one for an entry's
+first / last tile.  The general kernels stage the tile's source span with one bulk-async copy per CTA (UBLKCP) signalled
+on an mbarrier (SYNCS.*) and read it back with LDS.128; SHF.R.W funnel shifts re-align it (one code variant per word
+shift, hence the instruction count).  CCTL.E.PF2 is the L2 prefetch of the tile records.
+Local-memory instructions: none in the interior-tile paths.  The co-aligned kernels spill two keystream words (STL/LDL
+x2) in the predicated edge-tile path only; in the general kernels they belong to the out-of-line store_partial helper
+(caller-saved registers around the byte stores of an entry's partial first / last chunk: at most two calls per entry).
+No tcgen05 / HMMA: there is no contraction on this path (byte-wise integer cipher).""")
