@@ -84,9 +84,11 @@ def test_cycle_all_edge_keys(mb):
         assert (gpu_cycle(mb, data, key) == oracle.cycle(data, key)).all(), hex(key)
 
 
-def test_cycle_every_alignment_combination(mb):
-    """src and dst at every byte alignment, out of place; guard bytes around dst must survive."""
-    n = 5000
+@pytest.mark.parametrize("n", [5000, 41_003])
+def test_cycle_every_alignment_combination(mb, n):
+    """src and dst at every byte alignment, out of place; guard bytes around dst must survive.  5000 bytes
+    stay inside one (edge) tile; 41 003 bytes have interior tiles, which take the predicate-free copy of the
+    loop in each of its word-shift variants."""
     src_np = synth.payload(0, n + 64)
     src = DeviceBuffer.from_numpy(src_np)
     key = synth.PS3_KEY
