@@ -121,6 +121,9 @@ int32_t mod_key_jump(int32_t key, uint64_t pos);
  * give unspecified results (the reference never produces them). */
 int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint64_t dst_bytes,
                     uint32_t dst_align, mod_plan** out);
+/* Waits for the device (launches that still read the plan's records), then hands the records' HBM block back to
+ * a small per-device pool that the next mod_plan_create draws from -- cudaMalloc / cudaFree are not on the
+ * per-archive path.  mod_shutdown releases the pool. */
 int mod_plan_destroy(mod_plan* plan);
 uint64_t mod_plan_payload_bytes(const mod_plan* plan); /* sum of len */
 uint64_t mod_plan_num_tiles(const mod_plan* plan);

@@ -40,6 +40,18 @@ bool TraceEnabled()
     return lpValue && *lpValue && *lpValue != '0';
 }
 
+// Tracing aid: reports a pipeline operation that took longer than 50 ms (MOD_TRACE=1).
+struct SlowOp {
+    const char* mpWhat;
+    double mdStart;
+    explicit SlowOp(const char* lpWhat) : mpWhat(lpWhat), mdStart(TraceEnabled() ? NowSeconds() : 0.0) {}
+    ~SlowOp()
+    {
+        if (mdStart > 0.0 && NowSeconds() - mdStart > 0.05)
+            std::fprintf(stderr, "[mod] slow: %s took %.3f s\n", mpWhat, NowSeconds() - mdStart);
+    }
+};
+
 bool ReadWholeFile(const std::string& lPath, std::vector<unsigned char>& lOut)
 {
     FILE* lpFile = std::fopen(lPath.c_str(), "rb");
@@ -781,6 +793,7 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
         }
         for (int pp = 0; pp < liPieces; ++pp) {
             lReaders.Push([&, pp, luRange, kuPiece]() {
+                SlowOp lTimer("ExtractFiles read of an 8 MiB image piece");
                 const uint64_t luLo = (uint64_t)pp * kuPiece, luHi = std::min(luRange, luLo + kuPiece);
                 // the range keeps its (offset & 15) phase inside the pinned buffer, like on the device
                 if (!lRing.Failed() && luHi > luLo &&
@@ -796,7 +809,8 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
         const Group& lGroup = laGroups[gg];
         Slot& lSlot = lRing.maSlots[gg % lRing.maSlots.size()];
         thread_local std::unordered_set<std::string> lKnownDirectories;
-        if (!lRing.Failed() && lSlot.mbUsedGpu && mod_stream_sync(lSlot.mpStream) != MOD_OK) {
+        SlowOp lTimer("ExtractFiles writer task (stream sync + up to 48 files)");
+        if (!lRing.Failed() && lSlot.mbUsedGpu && [&]() { SlowOp lSync("ExtractFiles stream sync"); return mod_stream_sync(lSlot.mpStream); }() != MOD_OK) {
             std::cout << "GPU extract failed: " << mod_last_error() << "\n";
             lRing.Fail(eError_InvalidData);
         }
@@ -869,6 +883,7 @@ eError CArk::ExtractFiles(int liFirstFileIndex, int liNumFiles, const char* lpTa
                 while (laDevices[liDeviceIndex] != lSlot.miDevice)
                     ++liDeviceIndex;
                 uint64_t luTile0 = 0, luTile1 = 0;
+                SlowOp lTimer("ExtractFiles GPU enqueue of a group");
                 unsigned char* lpDevIn = (unsigned char*)lSlot.mpDevIn + (lGroup.srcLo & 15u);
                 unsigned char* lpDevOut = (unsigned char*)lSlot.mpDevOut + (lGroup.dstLo & 15u);
                 const bool lbOk =
@@ -1144,6 +1159,7 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
     auto lReadFiles = [&](size_t gg, size_t liFrom, size_t liTo) {
         const Group& lGroup = laGroups[gg];
         Slot& lSlot = lRing.maSlots[gg % lRing.maSlots.size()];
+        SlowOp lTimer("SaveArk reader task (up to 48 input files)");
         for (size_t ii = liFrom; ii < liTo && !lRing.Failed(); ++ii) {
             const Piece& lPiece = laPieces[ii];
             const modark::FileDef& lFile = mHeader.maFiles[lPiece.file];
@@ -1180,7 +1196,8 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
     auto lWriteRange = [&](size_t gg, size_t liTarget, uint64_t luLo, uint64_t luHi) {
         const Group& lGroup = laGroups[gg];
         Slot& lSlot = lRing.maSlots[gg % lRing.maSlots.size()];
-        if (!lRing.Failed() && lSlot.mbUsedGpu && mod_stream_sync(lSlot.mpStream) != MOD_OK) {
+        SlowOp lTimer("SaveArk writer task (stream sync + a 4 MiB range)");
+        if (!lRing.Failed() && lSlot.mbUsedGpu && [&]() { SlowOp lSync("SaveArk stream sync"); return mod_stream_sync(lSlot.mpStream); }() != MOD_OK) {
             std::cout << "GPU build failed: " << mod_last_error() << "\n";
             lRing.Fail(eError_InvalidData);
         }
@@ -1223,6 +1240,7 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
                 while (laDevices[liDeviceIndex] != lSlot.miDevice)
                     ++liDeviceIndex;
                 uint64_t luTile0 = 0, luTile1 = 0;
+                SlowOp lTimer("SaveArk GPU enqueue of a group");
                 unsigned char* lpDevIn = (unsigned char*)lSlot.mpDevIn + (lGroup.lo & 15u);
                 unsigned char* lpDevOut = (unsigned char*)lSlot.mpDevOut + (lGroup.lo & 15u);
                 const bool lbOk =
@@ -1268,10 +1286,11 @@ eError CArk::StreamBuiltImage(const std::vector<PartTarget>& laTargets) const
     }
     lReaders.Finish();
     lWriters.Finish();
+    const double ldDone = NowSeconds();
     lCleanup();
     if (TraceEnabled())
-        std::fprintf(stderr, "[mod] SaveArk: streamed %zu groups (%s): setup %.3f s, pipeline %.3f s\n", laGroups.size(),
-                     lbAnyKey ? "ciphered on the GPU" : "plain copy, no GPU", ldReady - ldStart, NowSeconds() - ldReady);
+        std::fprintf(stderr, "[mod] SaveArk: streamed %zu groups (%s): setup %.3f s, pipeline %.3f s, free %.3f s\n", laGroups.size(),
+                     lbAnyKey ? "ciphered on the GPU" : "plain copy, no GPU", ldReady - ldStart, ldDone - ldReady, NowSeconds() - ldDone);
     return (eError)lRing.miError.load();
 }
 

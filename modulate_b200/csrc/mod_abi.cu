@@ -84,7 +84,18 @@ struct DeviceCtx {
     uint64_t ws_descs_bytes = 0;
     void* ws_tiles = nullptr;
     uint64_t ws_tiles_bytes = 0;
+    // HBM blocks handed back by destroyed plans, kept for the next plan: cudaMalloc / cudaFree are device-wide
+    // synchronisation points that were seen to stall for 0.1-1 s inside a process that holds many other
+    // allocations, which is more than moving a whole archive costs
+    struct Block {
+        void* p;
+        uint64_t bytes;
+    };
+    std::mutex pool_mu;
+    std::vector<Block> pool;
 };
+constexpr size_t kPoolBlocks = 8;
+constexpr uint64_t kPoolMaxBlockBytes = 256ull << 20;
 
 DeviceCtx g_dev[kMaxDevices];
 std::mutex g_init_mu;
@@ -140,6 +151,12 @@ void release_ctx(DeviceCtx& c)  // current device == c.device
     }
     drop(c.ws_descs, c.ws_descs_bytes);
     drop(c.ws_tiles, c.ws_tiles_bytes);
+    {
+        std::lock_guard<std::mutex> lock(c.pool_mu);
+        for (DeviceCtx::Block& b : c.pool)
+            cudaFree(b.p);
+        c.pool.clear();
+    }
     if (c.h_descs)
         cudaFreeHost(c.h_descs);
     c.h_descs = nullptr;
@@ -255,6 +272,52 @@ int grow_pinned(void** buf, uint64_t* have, uint64_t need)
     }
     *have = need;
     return MOD_OK;
+}
+
+// Plan scratch from the device's block pool (current device == c.device).  A cached block serves a request
+// it is not more than 4x too large for; *got receives the block's real size for pool_free.
+cudaError_t pool_alloc(DeviceCtx& c, uint64_t bytes, void** out, uint64_t* got)
+{
+    bytes = std::max<uint64_t>(256, (bytes + 255) & ~255ull);
+    {
+        std::lock_guard<std::mutex> lock(c.pool_mu);
+        size_t best = c.pool.size();
+        for (size_t i = 0; i < c.pool.size(); ++i)
+            if (c.pool[i].bytes >= bytes && c.pool[i].bytes / 4 <= bytes && (best == c.pool.size() || c.pool[i].bytes < c.pool[best].bytes))
+                best = i;
+        if (best != c.pool.size()) {
+            *out = c.pool[best].p;
+            *got = c.pool[best].bytes;
+            c.pool.erase(c.pool.begin() + (long)best);
+            return cudaSuccess;
+        }
+    }
+    *got = bytes;
+    return cudaMalloc(out, bytes);
+}
+
+void pool_free(DeviceCtx& c, void* p, uint64_t bytes)
+{
+    if (!p)
+        return;
+    if (bytes <= kPoolMaxBlockBytes && c.ready.load(std::memory_order_acquire)) {
+        std::lock_guard<std::mutex> lock(c.pool_mu);
+        if (c.pool.size() >= kPoolBlocks) {  // full: the smallest cached block makes room if this one is larger
+            size_t smallest = 0;
+            for (size_t i = 1; i < c.pool.size(); ++i)
+                if (c.pool[i].bytes < c.pool[smallest].bytes)
+                    smallest = i;
+            if (c.pool[smallest].bytes < bytes) {
+                cudaFree(c.pool[smallest].p);
+                c.pool[smallest] = DeviceCtx::Block{p, bytes};
+                return;
+            }
+        } else {
+            c.pool.push_back(DeviceCtx::Block{p, bytes});
+            return;
+        }
+    }
+    cudaFree(p);
 }
 
 // One launch (or a few, beyond 64 pieces) of the batched kernel over a contiguous stream.
@@ -771,6 +834,7 @@ struct mod_plan {
     uint32_t n_tiles = 0;
     int32_t uniform_delta = -1;  // (src_off - dst_off) & 15 if all entries agree: selects the co-aligned kernel
     modk::TileRec* d_tiles = nullptr;
+    uint64_t d_tiles_bytes = 0;         // size of the pool block behind d_tiles
     std::vector<mod_desc> descs;        // host copy: window validation, tile ranges
     std::vector<uint32_t> first_tile;   // n + 1 entries
 };
@@ -1024,9 +1088,10 @@ int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint6
     p->n_tiles = (uint32_t)tiles;
     p->uniform_delta = uniform_delta_of(descs, n);
     modk::DevDesc* d_descs = nullptr;  // only needed while the tile records are built
+    uint64_t d_descs_bytes = 0;
     auto cleanup = [&]() {
-        if (d_descs) cudaFree(d_descs);
-        if (p->d_tiles) cudaFree(p->d_tiles);
+        pool_free(*c, d_descs, d_descs_bytes);
+        pool_free(*c, p->d_tiles, p->d_tiles_bytes);
         delete p;
     };
     try {
@@ -1040,9 +1105,9 @@ int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint6
         throw;
     }
     if (n && tiles) {
-        cudaError_t e = cudaMalloc((void**)&d_descs, n * sizeof(modk::DevDesc));
+        cudaError_t e = pool_alloc(*c, n * sizeof(modk::DevDesc), (void**)&d_descs, &d_descs_bytes);
         if (e == cudaSuccess)
-            e = cudaMalloc((void**)&p->d_tiles, tiles * sizeof(modk::TileRec));
+            e = pool_alloc(*c, tiles * sizeof(modk::TileRec), (void**)&p->d_tiles, &p->d_tiles_bytes);
         if (e != cudaSuccess) {
             cudaGetLastError();
             cleanup();
@@ -1059,7 +1124,7 @@ int mod_plan_create(const mod_desc* descs, uint64_t n, uint64_t src_bytes, uint6
             cleanup();
             return fail(MOD_ERR_CUDA, "mod_plan_create: %s", cudaGetErrorString(e));
         }
-        cudaFree(d_descs);
+        pool_free(*c, d_descs, d_descs_bytes);
         d_descs = nullptr;
     }
     *out = p;
@@ -1074,7 +1139,11 @@ int mod_plan_destroy(mod_plan* plan)
     if (plan->d_tiles) {
         DeviceGuard guard;
         guard.enter(plan->device);
-        cudaFree(plan->d_tiles);
+        cudaDeviceSynchronize();  // launches that still read the records finish first (what cudaFree used to guarantee)
+        if (plan->device >= 0 && plan->device < kMaxDevices)
+            pool_free(g_dev[plan->device], plan->d_tiles, plan->d_tiles_bytes);  // back to the device's block pool
+        else
+            cudaFree(plan->d_tiles);
     }
     delete plan;
     return MOD_OK;
