@@ -493,7 +493,8 @@ def piece_count(descs: np.ndarray, group: int = 16 * MIB) -> int:
     return int(np.where(n > group + group // 2, np.maximum(1, n // group), 1).sum())
 
 
-def measure_workload(c: Ctx, args, workload: str, *, full: bool, cfg4_n: int = 1_000_000, sustain_s: float = 3.0) -> dict:
+def measure_workload(c: Ctx, args, workload: str, *, full: bool, cfg4_n: int = 1_000_000, sustain_s: float = 3.0,
+                     cooldown_s: float = 0.0) -> dict:
     """Device-resident value, per-launch roofline, parity, the sustained run (`sustain_s` seconds of back-to-back
     launches; 0 = skip) and, if `full`, e2e for one workload."""
     torch, mb = c.torch, c.mb
@@ -538,6 +539,9 @@ def measure_workload(c: Ctx, args, workload: str, *, full: bool, cfg4_n: int = 1
     checked_total = int(c.reduce(float(checked), "sum"))
     step(None)  # in-place sets: back to plaintext (the cipher is an involution)
 
+    if cooldown_s > 0:  # generating tens of GiB of payload is power-hungry too: idle until the power controller's
+        torch.cuda.synchronize()  # averaging window has forgotten it, so the burst figure is a burst figure
+        time.sleep(cooldown_s)
     ms_total, kernel_ms, clock_info, launches = timed_steps(c, step, kernel, args.steps, args.warmup)
     total_payload = int(gdescs["len"].sum())
     value = (total_payload + (HDR_BYTES - 4)) * args.steps / (ms_total * 1e-3) / 1e9
@@ -780,8 +784,7 @@ def run_gpu_arm(args) -> None:
                     # burst figure from a SHORT timed region (a cfg4 step moves 67 GB: 20 of them run into the board's
                     # power cap half way and the "burst" number becomes a mixture), then the sustained run
                     sub_args.steps = max(5, min(args.steps, 20 if w == "cfg2" else 5))
-                    time.sleep(1.0)  # let the power-cap controller's averaging window forget the previous leg
-                    r = measure_workload(c, sub_args, w, full=False, sustain_s=1.5)
+                    r = measure_workload(c, sub_args, w, full=False, sustain_s=1.5, cooldown_s=1.5)
                     extra[w] = {k: r[k] for k in ("value", "ms_per_step", "kernel_ms", "parity_bytes_checked",
                                                   "roofline", "config", "gpu_launches", "clocks")}
                     extra[w]["steps"] = sub_args.steps

@@ -49,7 +49,11 @@ using modlcg::low8_canonical;
 #define MODK_CANON_FMA_MASK 0x5  // exact path: which of every 4 bytes canonicalise on the FMA pipe (IMAD.HI) vs ALU (LEA.HI)
 #endif
 #ifndef MODK_MIN_CTAS
-#define MODK_MIN_CTAS 8          // GENERAL kernels (any source alignment): resident CTAs per SM (64 registers)
+#define MODK_MIN_CTAS 10         // GENERAL kernels (any source alignment): resident CTAs per SM (48 registers)
+#endif
+#ifndef MODK_MIN_CTAS_INLINE
+#define MODK_MIN_CTAS_INLINE 8   // general CONTIGUOUS kernel (out-of-place Cycle between misaligned buffers): it also computes its
+                                 // tile record, which does not fit 48 registers without spilling
 #endif
 #ifndef MODK_MIN_CTAS_COAL
 #define MODK_MIN_CTAS_COAL 10    // CO-ALIGNED kernels (source and destination agree mod 16, e.g. in place): 48 registers
@@ -57,6 +61,10 @@ using modlcg::low8_canonical;
 #ifndef MODK_STAGE
 #define MODK_STAGE 1             // general kernels: 1 = the tile's source span is staged through shared memory by ONE
                                  // bulk-async copy per CTA (cp.async.bulk + mbarrier), 0 = two LDG.128 per chunk into registers
+#endif
+#ifndef MODK_STAGE_SEQ
+#define MODK_STAGE_SEQ 1         // general kernels: read the staged granules chunk by chunk inside the store loop: 8 registers of
+                                 // granules live instead of 32, which is what lets them run at 10 CTAs/SM without spilling
 #endif
 #ifndef MODK_GENERAL_FULL
 #define MODK_GENERAL_FULL 1      // general kernels: separate predicate-free code for interior tiles (doubles their code size)
@@ -233,7 +241,8 @@ __device__ __noinline__ void slow_chunk(uint64_t src_byte0, uint64_t dst_chunk, 
 // starts kWs words (+ `bs` / 8 bytes) into its first granule and straddles two.
 // kStaged: the tile's source span has been requested into shared memory by one bulk-async copy
 // (issued by thread 0 in run_tile); the granules are read from there AFTER the keystream has been
-// generated, so no register holds a load in flight.
+// generated, so no register holds a load in flight; they are read chunk by chunk inside the store loop
+// (MODK_STAGE_SEQ), shared memory being close enough that nothing is gained by batching the reads.
 // kFull: the tile is a whole 512 chunks and none of them is partial (every tile of a big entry but its first
 // and last): no per-chunk predicates on loads or stores at all.
 template <int kWs, int U, bool kStaged, bool kFull = false>
@@ -295,19 +304,25 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
     const bool redo = (any & 0x80800000u) != 0u;
 
 #if MODK_STAGE
+    auto load_staged = [&](const int u) {  // chunk u's granules out of the shared-memory stage
+        own[u] = make_uint4(0u, 0u, 0u, 0u);
+        nxt[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (kFull || idx0 + (uint32_t)u * T < n_valid) {
+            own[u] = lds128(stage + 16u * (idx0 + (uint32_t)u * T));
+            if (kWs >= 0)
+                nxt[u] = lds128(stage + 16u * (idx0 + (uint32_t)u * T) + 16u);
+        }
+    };
     if (kStaged) {
         mbar_wait(bar, 0u);  // the CTA's only use of the barrier: phase 0
+#if !MODK_STAGE_SEQ
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            own[u] = make_uint4(0u, 0u, 0u, 0u);
-            nxt[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (kFull || idx0 + (uint32_t)u * T < n_valid) {
-                own[u] = lds128(stage + 16u * (idx0 + (uint32_t)u * T));
-                if (kWs >= 0)
-                    nxt[u] = lds128(stage + 16u * (idx0 + (uint32_t)u * T) + 16u);
-            }
-        }
+        for (int u = 0; u < U; ++u)
+            load_staged(u);
+#endif
     }
+#else
+    auto load_staged = [&](const int) {};
 #endif
 
     const uint32_t f_lo = head ? 1u : 0u;
@@ -333,6 +348,13 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
             store_partial(dp + 16ull * T * u, out, idx == 0u ? head : 0u, idx + 1u == n_valid ? tail : 16u);
     };
     if (__builtin_expect(redo, 0)) {
+#if MODK_STAGE_SEQ
+        if (kStaged) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                load_staged(u);
+        }
+#endif
         // some state of this thread's chunks needed a canonical subtract (~1 thread in 2 000): redo all four
         // exactly, from start states recomputed here (nothing is kept live for this path)
 #pragma unroll 1
@@ -353,6 +375,10 @@ __device__ __forceinline__ void process_tile(const uint64_t src_tile, const uint
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+#if MODK_STAGE_SEQ
+        if (kStaged)
+            load_staged(u);  // one chunk at a time: 8 registers of granules live instead of 32
+#endif
         const uint4 data = source(u);
         emit(u, make_uint4(data.x ^ ks[u][0], data.y ^ ks[u][1], data.z ^ ks[u][2], data.w ^ ks[u][3]));
     }
@@ -523,7 +549,7 @@ cycle_batch_kernel(const BatchArgs a)
 // from the constant-bank jump tables instead of being loaded.  (A short buffer such as the 384 KiB
 // HDR is 48 CTAs that all run at once, each thread's 4 chains interleaved: one chain latency.)
 template <bool kGeneral>
-__global__ void __launch_bounds__(kThreadsPerCta, kGeneral ? MODK_MIN_CTAS : MODK_MIN_CTAS_COAL)
+__global__ void __launch_bounds__(kThreadsPerCta, kGeneral ? MODK_MIN_CTAS_INLINE : MODK_MIN_CTAS_COAL)
 cycle_inline_kernel(const BatchArgs a, const __grid_constant__ InlineDescs in)
 {
     MODK_STAGE_SETUP

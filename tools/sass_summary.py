@@ -56,6 +56,8 @@ first / last tile.  The general kernels stage the tile's source span with one bu
 on an mbarrier (SYNCS.*) and read it back with LDS.128; SHF.R.W funnel shifts re-align it (one code variant per word
 shift, hence the instruction count).  CCTL.E.PF2 is the L2 prefetch of the tile records.
 Local-memory instructions: none in the interior-tile paths.  The co-aligned kernels spill two keystream words (STL/LDL
-x2) in the predicated edge-tile path only; in the general kernels they belong to the out-of-line store_partial helper
-(caller-saved registers around the byte stores of an entry's partial first / last chunk: at most two calls per entry).
+x2) in the predicated edge-tile path only; the general kernels (48 registers since they run at 10 CTAs/SM) spill one to
+three words in the edge-tile copies of the loop, and 18 of their local-memory instructions belong to the out-of-line
+store_partial helper (caller-saved registers around the byte stores of an entry's partial first / last chunk: at most
+two calls per entry).
 No tcgen05 / HMMA: there is no contraction on this path (byte-wise integer cipher).""")
