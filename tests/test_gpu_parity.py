@@ -248,6 +248,47 @@ def test_batch_in_place_and_plan_reuse(mb):
     buf.free()
 
 
+def test_plan_records_come_from_a_block_pool(mb):
+    """mod_plan_destroy hands the plan's HBM records to a per-device pool and the next mod_plan_create may reuse
+    the block (cudaMalloc / cudaFree stay off the per-archive path).  Plans of shrinking, growing and equal sizes,
+    created and destroyed in turn and two alive at once, must each produce the oracle's bytes; mod_shutdown
+    releases the pool and the library comes back up afterwards."""
+    from modulate_b200 import _abi
+    rng = np.random.default_rng(77)
+    src_np = synth.payload(3, 6 << 20)
+
+    def case(n, max_len, seed):
+        sizes = np.random.default_rng(seed).integers(1, max_len, size=n).astype(np.int64)
+        scale = min(1.0, (5 << 20) / float(sizes.sum()))
+        sizes = np.maximum(1, (sizes * scale).astype(np.int64))
+        off = synth.packed_offsets(sizes) + 5
+        return mb.make_descs(off, off - 5, sizes, synth.entry_keys(n, seed=seed))
+
+    src = DeviceBuffer.from_numpy(src_np)
+    held = None
+    for i, (n, max_len) in enumerate([(4000, 3000), (50, 200000), (3000, 4000), (7, 900000), (4000, 3000), (1, 100)]):
+        descs = case(n, max_len, 200 + i)
+        dst_np = np.full(6 << 20, 0x3C, np.uint8)
+        want = oracle.cycle_batch(descs, src_np, dst_np.copy())
+        dst = DeviceBuffer.from_numpy(dst_np)
+        plan = mb.Plan(descs, src_np.size, dst_np.size)
+        plan.run(src.ptr, dst.ptr)
+        sync()
+        assert (dst.download() == want).all(), i
+        dst.free()
+        if held is not None:
+            held.close()
+        held = plan if i % 2 == 0 else None  # every other plan stays alive while the next one is built
+        if held is None:
+            plan.close()
+    if held is not None:
+        held.close()
+    src.free()
+    _abi.load().mod_shutdown()  # frees the pool with everything else; the next call re-creates the context
+    data = synth.payload(9, 100_000)
+    assert (gpu_cycle(mb, data, 0x1234567) == oracle.cycle(data, 0x1234567)).all()
+
+
 def test_batch_identity_key_is_plain_copy(mb):
     """key == 0 (mod m) is the reference's plain extract: ExtractFiles' fwrite (CArk.cpp:494)."""
     sizes = np.array([1, 100, 4096, 70001, 33], np.int64)
