@@ -289,8 +289,20 @@ void PrintUsage()
 
 }  // namespace
 
+// MOD_TRACE=1: wall-clock stamps of the process phases (a cold start is dominated by CUDA context creation and
+// page-locking, not by the archive work; tools/cli_timing.sh reads these).
+static void TraceStamp(const char* lpWhat)
+{
+    const char* lpTrace = std::getenv("MOD_TRACE");
+    if (!lpTrace || !*lpTrace || *lpTrace == '0')
+        return;
+    const double ldNow = std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count();
+    std::fprintf(stderr, "[mod] cli %s at %.3f\n", lpWhat, ldNow);
+}
+
 int main(int argc, char* argv[])
 {
+    TraceStamp("main entered");
     struct sCommandPair {
         const char* mpCommandName;
         std::function<eError(std::deque<std::string>&)> mFunction;
@@ -316,6 +328,7 @@ int main(int argc, char* argv[])
                 continue;
             lbMatched = true;
             laParams.pop_front();
+            TraceStamp(lCommand.mpCommandName);
             const eError leError = lCommand.mFunction(laParams);
             if (leError != eError_NoError) {
                 ShowError(leError);
@@ -331,5 +344,6 @@ int main(int argc, char* argv[])
         }
     }
     std::cout << "Complete!\n";
+    TraceStamp("main returns");
     return 0;
 }

@@ -177,7 +177,12 @@ void release_ctx(DeviceCtx& c)  // current device == c.device
 int acquire(int device, DeviceCtx** out)
 {
     int count = 0;
+    static std::atomic<bool> first_call{true};
+    const bool trace_init = first_call.exchange(false) && env_u64("MOD_TRACE", 0) != 0;
+    const double t_first = trace_init ? now_ms() : 0.0;
     CUDA_TRY(cudaGetDeviceCount(&count));
+    if (trace_init)
+        fprintf(stderr, "[mod] first CUDA call (driver initialisation): %.1f ms\n", now_ms() - t_first);
     if (count <= 0)
         return fail(MOD_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
     if (device >= 0) {
@@ -194,7 +199,10 @@ int acquire(int device, DeviceCtx** out)
         std::lock_guard<std::mutex> lock(g_init_mu);
         if (!c.ready.load(std::memory_order_relaxed)) {
             c.device = cur;
+            const double t_ctx = now_ms();
             CUDA_TRY(modk::upload_tables());
+            if (env_u64("MOD_TRACE", 0) != 0)
+                fprintf(stderr, "[mod] device %d: context + module load + jump tables: %.1f ms\n", cur, now_ms() - t_ctx);
             for (int i = 0; i < kPipeSlots; ++i)
                 if (!c.pipe_stream[i])
                     CUDA_TRY(cudaStreamCreateWithFlags(&c.pipe_stream[i], cudaStreamNonBlocking));
