@@ -177,12 +177,7 @@ void release_ctx(DeviceCtx& c)  // current device == c.device
 int acquire(int device, DeviceCtx** out)
 {
     int count = 0;
-    static std::atomic<bool> first_call{true};
-    const bool trace_init = first_call.exchange(false) && env_u64("MOD_TRACE", 0) != 0;
-    const double t_first = trace_init ? now_ms() : 0.0;
     CUDA_TRY(cudaGetDeviceCount(&count));
-    if (trace_init)
-        fprintf(stderr, "[mod] first CUDA call (driver initialisation): %.1f ms\n", now_ms() - t_first);
     if (count <= 0)
         return fail(MOD_ERR_CUDA, "no CUDA device visible: this library has no CPU fallback");
     if (device >= 0) {

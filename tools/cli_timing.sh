@@ -22,7 +22,7 @@ import re, sys
 s, e = float(sys.argv[1]), float(sys.argv[2]); t = open(sys.argv[3]).read()
 st = {m.group(1): float(m.group(2)) for m in re.finditer(r"\[mod\] cli (.+?) at ([0-9.]+)", t)}
 print("    exec -> main %.3f s, main -> return %.3f s, return -> process gone %.3f s;" % (st["main entered"] - s, st["main returns"] - st["main entered"], e - st["main returns"]),
-      "; ".join(l[6:] for l in t.splitlines() if "first CUDA call" in l or "context +" in l))
+      "; ".join(l[6:] for l in t.splitlines() if "context +" in l))
 PY
   s=$(date +%s.%N); MOD_TRACE=1 $CLI -bodykey 195948557 -packall -pack_add out re 2> trace_p.txt > /dev/null; e=$(date +%s.%N)
   echo "pack   wall $(python -c "print('%.3f' % ($e - $s))") s   $(grep 'SaveArk:' trace_p.txt | sed 's/.*): //')"
