@@ -62,6 +62,9 @@ using modlcg::low8_canonical;
 #define MODK_STAGE 1             // general kernels: 1 = the tile's source span is staged through shared memory by ONE
                                  // bulk-async copy per CTA (cp.async.bulk + mbarrier), 0 = two LDG.128 per chunk into registers
 #endif
+#ifndef MODK_EDGE_ROUNDS
+#define MODK_EDGE_ROUNDS 1       // co-aligned kernels: a partly filled tile runs only the rounds (of 128 chunks) that hold chunks
+#endif
 #ifndef MODK_STAGE_SEQ
 #define MODK_STAGE_SEQ 1         // general kernels: read the staged granules chunk by chunk inside the store loop: 8 registers of
                                  // granules live instead of 32, which is what lets them run at 10 CTAs/SM without spilling
@@ -421,6 +424,24 @@ __device__ __forceinline__ void run_tile(const BatchArgs& a, const int64_t src_r
 
     const uint32_t bs = (shift & 3u) * 8u;
     if (!kGeneral) {
+#if MODK_EDGE_ROUNDS
+        // A partly filled tile (the last tile of an entry, every tile of a small one) only runs the rounds that
+        // hold chunks (CTA-uniform): with many small entries about half of every last tile is empty, and a
+        // keystream generated for chunks that do not exist is instructions and power for nothing.
+        if (U == 4 && n_valid <= 3u * (uint32_t)kThreadsPerCta) {
+            if (n_valid <= (uint32_t)kThreadsPerCta) {
+                const uint32_t p1[1] = {pw[0]};
+                process_tile<-1, 1, false, false>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, p1, a.two, stage, bar);
+            } else if (n_valid <= 2u * (uint32_t)kThreadsPerCta) {
+                const uint32_t p2[2] = {pw[0], pw[1]};
+                process_tile<-1, 2, false, false>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, p2, a.two, stage, bar);
+            } else {
+                const uint32_t p3[3] = {pw[0], pw[1], pw[2]};
+                process_tile<-1, 3, false, false>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, p3, a.two, stage, bar);
+            }
+            return;
+        }
+#endif
         process_tile<-1, U, false, false>(src_tile, dst_tile, st, n_valid, head, tail, bs, idx0, pw, a.two, stage, bar);
         return;
     }
