@@ -55,8 +55,10 @@ thread for 64 bytes = 4.4 per byte, ncu: 2.38e9 warp instructions for 16 GiB) an
 first / last tile.  The general kernels stage the tile's source span with one bulk-async copy per CTA (UBLKCP) signalled
 on an mbarrier (SYNCS.*) and read it back with LDS.128; SHF.R.W funnel shifts re-align it (one code variant per word
 shift, hence the instruction count).  CCTL.E.PF2 is the L2 prefetch of the tile records.
-Local-memory instructions: none in the interior-tile paths.  The co-aligned kernels spill two keystream words (STL/LDL
-x2) in the predicated edge-tile path only; the general kernels (48 registers since they run at 10 CTAs/SM) spill one to
+The co-aligned kernels carry three more copies of the predicated loop, with 1, 2 and 3 rounds of 128 chunks, for partly
+filled tiles.
+Local-memory instructions: none in the interior-tile paths.  The co-aligned kernels spill one keystream word (STL + LDL)
+in the four-round predicated edge-tile copy only; the general kernels (48 registers since they run at 10 CTAs/SM) spill one to
 three words in the edge-tile copies of the loop, and 18 of their local-memory instructions belong to the out-of-line
 store_partial helper (caller-saved registers around the byte stores of an entry's partial first / last chunk: at most
 two calls per entry).
