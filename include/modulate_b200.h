@@ -176,6 +176,17 @@ int mod_shard_range(uint64_t total, int rank, int world, uint64_t* begin, uint64
 int64_t mod_shard_descs(const mod_desc* descs, uint64_t n, int rank, int world, mod_desc* out,
                         uint64_t out_cap);
 
+/* How the host-pointer batch path (mod_cycle_batch on host buffers) cuts a descriptor list into pipeline
+ * groups of ~group_bytes of payload: group boundaries fall on destination addresses with
+ * (dst_phase + dst_off) % modulus == 0 INSIDE entries (modulus a power of two >= 16; the library uses 128 and
+ * the low bits of the caller's dst pointer, because pinned <-> HBM copies only run at full speed between
+ * 128-byte aligned addresses); a piece that starts `pos` bytes into its entry carries the jumped key.
+ * Writes the pieces to `out` and, per piece, whether a group ends after it to `closes` (capacity out_cap each;
+ * pass out == NULL to query the count).  Returns the number of pieces, or a negative MOD_ERR_*.  Host logic, no
+ * GPU needed (exposed so the cut can be tested and reproduced). */
+int64_t mod_group_descs(const mod_desc* descs, uint64_t n, uint64_t group_bytes, uint64_t dst_phase, uint64_t modulus,
+                        mod_desc* out, uint8_t* closes, uint64_t out_cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,8 +15,8 @@ over that C ABI, mirroring the reference's operator interface for the path:
 Nothing here computes keystream on the CPU; every call goes through the CUDA library and raises
 ``ModError`` if no GPU is usable.
 """
-from .api import (ArkError, CEncryptionCycler, DESC_DTYPE, ModError, Plan, cycle, cycle_batch, cycle_batch_sharded,
+from .api import (ArkError, CEncryptionCycler, DESC_DTYPE, ModError, Plan, cycle, cycle_batch, cycle_batch_sharded, group_descs,
                   cycle_device, cycle_sharded, ark_pack, ark_unpack, dta_set_int, device_count, init, key_jump, launch_count, make_descs, shard_descs, shard_range)
 
-__all__ = ["ArkError", "ark_pack", "ark_unpack", "dta_set_int", "CEncryptionCycler", "DESC_DTYPE", "ModError", "Plan", "cycle", "cycle_batch", "cycle_batch_sharded", "cycle_device", "cycle_sharded",
+__all__ = ["ArkError", "ark_pack", "ark_unpack", "dta_set_int", "CEncryptionCycler", "DESC_DTYPE", "ModError", "Plan", "cycle", "cycle_batch", "cycle_batch_sharded", "group_descs", "cycle_device", "cycle_sharded",
            "device_count", "init", "key_jump", "launch_count", "make_descs", "shard_descs", "shard_range"]

@@ -216,6 +216,20 @@ def shard_descs(descs: np.ndarray, rank: int, world: int) -> np.ndarray:
     return out
 
 
+def group_descs(descs: np.ndarray, group_bytes: int, dst_phase: int = 0, modulus: int = 128):
+    """The pieces the host-pointer batch path cuts a descriptor list into and, per piece, whether a pipeline
+    group ends after it (mod_group_descs; host logic)."""
+    d = _descs(descs)
+    L = _abi.load()
+    ptr = d.ctypes.data if len(d) else None
+    n = _abi.check(L.mod_group_descs(ptr, len(d), group_bytes, dst_phase, modulus, None, None, 0))
+    out = np.zeros(n, dtype=DESC_DTYPE)
+    closes = np.zeros(n, dtype=np.uint8)
+    if n:
+        _abi.check(L.mod_group_descs(ptr, len(d), group_bytes, dst_phase, modulus, out.ctypes.data, closes.ctypes.data, n))
+    return out, closes
+
+
 # ---- archive-level facade (include/modulate_ark.h): the reference's Unpack / Pack command bodies ----------
 
 class ArkError(RuntimeError):

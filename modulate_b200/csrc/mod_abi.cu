@@ -21,6 +21,7 @@
 #include <thread>
 #include <vector>
 
+#include "batch_cut.h"
 #include "cycle_kernels.cuh"
 #include "lcg.h"
 
@@ -32,6 +33,7 @@ namespace {
 constexpr int kPipeSlots = MOD_PIPE_SLOTS;  // slices / groups in flight on the host-pointer paths
 constexpr uint64_t kMaxPiece = 1ull << 30;  // a contiguous stream is cut into <= 1 GiB pieces
 constexpr int kMaxDevices = 64;
+constexpr uint64_t kCopyAlign = 128;        // pinned <-> HBM copies run ~13 % faster between 128-byte aligned addresses
 
 thread_local std::string tl_error = "";
 std::atomic<uint64_t> g_launches{0};
@@ -386,9 +388,12 @@ int cycle_host(DeviceCtx& c, uint8_t* host, uint64_t len, int32_t key)
     int rc = MOD_OK;
     cudaError_t e = cudaSuccess;
     uint64_t pos = 0;
+    // a long buffer that does not start on a 128-byte boundary gets a short first slice, so that every other
+    // slice is copied between 128-byte aligned addresses (see kCopyAlign)
+    const uint64_t head = len >= 4 * slice ? ((kCopyAlign - ((uintptr_t)host & (kCopyAlign - 1))) & (kCopyAlign - 1)) : 0;
     for (uint64_t i = 0; pos < len && rc == MOD_OK && e == cudaSuccess; ++i) {
         const int slot = (int)(i % kPipeSlots);
-        const uint64_t n = std::min(slice, len - pos);
+        const uint64_t n = i == 0 && head ? head : std::min(slice, len - pos);
         cudaStream_t s = c.pipe_stream[slot];
         uint8_t* d = (uint8_t*)c.slice_buf[slot];
         e = cudaMemcpyAsync(d, host + pos, n, cudaMemcpyHostToDevice, s);
@@ -490,35 +495,16 @@ int batch_host(DeviceCtx& c, const mod_desc* user_descs, uint64_t user_n, const 
     if (rc != MOD_OK)
         return rc;
 
-    // entries larger than a group are cut at 16-byte destination boundaries; the pieces continue
-    // the entry's keystream through jumped keys
-    const uint64_t group_bytes = std::max<uint64_t>(1 << 20, env_u64("MOD_GROUP_BYTES", 16ull << 20)) & ~15ull;
-    std::vector<mod_desc> cut;
-    bool any_big = false;
-    for (uint64_t i = 0; i < user_n && !any_big; ++i)
-        any_big = user_descs[i].len > group_bytes + (group_bytes >> 1);
-    if (any_big) {
-        cut.reserve(user_n + 64);
-        for (uint64_t i = 0; i < user_n; ++i) {
-            const mod_desc& d = user_descs[i];
-            if (d.len <= group_bytes + (group_bytes >> 1)) {
-                cut.push_back(d);
-                continue;
-            }
-            const uint32_t k0 = modlcg::key_residue(d.key);
-            uint64_t pos = 0;
-            while (pos < d.len) {
-                uint64_t take = std::min<uint64_t>(group_bytes - ((d.dst_off + pos) & 15u), d.len - pos);
-                if (d.len - pos - take < (group_bytes >> 1))
-                    take = d.len - pos;  // no short tail piece
-                cut.push_back(mod_desc{d.src_off + pos, d.dst_off + pos, (uint32_t)take,
-                                       (int32_t)modlcg::mulmod(k0, modlcg::pow_a(pos))});
-                pos += take;
-            }
-        }
-    }
-    const mod_desc* descs = any_big ? cut.data() : user_descs;
-    const uint64_t n = any_big ? cut.size() : user_n;
+    // the descriptor list is cut into groups of ~group_bytes of payload whose boundaries fall on aligned
+    // destination addresses INSIDE entries (batch_cut.h); pieces continue their entry's keystream through
+    // jumped keys.  The alignment is that of the host address when the caller's buffers allow aligned copies.
+    const uint64_t group_bytes = std::max<uint64_t>(1 << 20, env_u64("MOD_GROUP_BYTES", 16ull << 20)) & ~(kCopyAlign - 1);
+    const bool align_copies = (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0u && env_u64("MOD_ALIGN_COPIES", 1) != 0;
+    modcut::Cut cut;
+    modcut::cut_into_groups(user_descs, user_n, group_bytes, align_copies ? (uint64_t)((uintptr_t)dst & (kCopyAlign - 1)) : 0,
+                            align_copies ? kCopyAlign : 16, cut);
+    const mod_desc* descs = cut.pieces.data();
+    const uint64_t n = cut.pieces.size();
     if (n >= 0xFFFFFFFFull)
         return fail(MOD_ERR_ARG, "mod_cycle_batch: too many descriptors (%llu)", (unsigned long long)n);
 
@@ -551,7 +537,6 @@ int batch_host(DeviceCtx& c, const mod_desc* user_descs, uint64_t user_n, const 
     };
     {
         Group g{0, 0, 0, 0, UINT64_MAX, 0, UINT64_MAX, 0};
-        uint64_t acc = 0;
         uint32_t tile = 0;
         for (uint64_t i = 0; i < n; ++i) {
             const mod_desc& d = descs[i];
@@ -561,15 +546,13 @@ int batch_host(DeviceCtx& c, const mod_desc* user_descs, uint64_t user_n, const 
                 g.d_lo = std::min(g.d_lo, d.dst_off);
                 g.d_hi = std::max(g.d_hi, d.dst_off + d.len);
             }
-            acc += d.len;
             tile += modk::tiles_for_entry((uint32_t)(d.dst_off & 15u), d.len);
-            if (acc >= group_bytes || i + 1 == n) {
+            if (cut.closes[i]) {
                 g.e1 = i + 1;
                 g.t1 = tile;
                 if (g.t1 > g.t0)
                     groups.push_back(g);
                 g = Group{i + 1, 0, tile, 0, UINT64_MAX, 0, UINT64_MAX, 0};
-                acc = 0;
             }
         }
     }
@@ -667,13 +650,19 @@ int batch_host(DeviceCtx& c, const mod_desc* user_descs, uint64_t user_n, const 
         whole();
 
     // slot buffers: the source window keeps its (offset & 15) phase and the destination window starts
-    // at a 16-byte boundary of the destination space, so host co-alignment survives on the device
+    // at a 16-byte boundary of the destination space, so host co-alignment survives on the device.
+    // Beyond that, pinned <-> HBM copies only run at full speed when both addresses are 128-byte aligned
+    // (tools/copy_align_probe.py: 47 GB/s each way against 41 at any smaller phase), and groups of
+    // byte-packed entries start anywhere: with 16-byte aligned caller buffers a window therefore sits at the
+    // phase (host address & 127) in its slot, uploads are widened to 128-byte boundaries of the host address
+    // (a few source bytes more) and downloads are split into an aligned body and up to two short ends.
+    const bool split_downloads = env_u64("MOD_SPLIT_DOWNLOADS", 1) != 0;
     const int slots = (int)std::min<size_t>(kPipeSlots, groups.size());
     {
         uint64_t s_need = 0, d_need = 0;
         for (const Group& g : groups) {
-            s_need = std::max<uint64_t>(s_need, (g.s_lo & 15u) + (g.s_hi - g.s_lo));
-            d_need = std::max<uint64_t>(d_need, g.d_hi - (g.d_lo & ~15ull));
+            s_need = std::max<uint64_t>(s_need, (g.s_lo & 15u) + (g.s_hi - g.s_lo) + 3 * kCopyAlign);
+            d_need = std::max<uint64_t>(d_need, g.d_hi - (g.d_lo & ~15ull) + kCopyAlign);
         }
         for (int k = 0; k < slots; ++k) {
             if ((rc = grow(&c.slot_src[k], &c.slot_src_bytes[k], s_need)) != MOD_OK)
@@ -706,10 +695,18 @@ int batch_host(DeviceCtx& c, const mod_desc* user_descs, uint64_t user_n, const 
         const Group& g = groups[gi];
         const int k = (int)(gi % (size_t)slots);
         cudaStream_t s = c.pipe_stream[k];
-        uint8_t* win_src = (uint8_t*)c.slot_src[k] + (g.s_lo & 15u);  // holds source bytes [s_lo, s_hi)
-        uint8_t* win_dst = (uint8_t*)c.slot_dst[k];                    // holds destination bytes [d_lo16, d_hi)
         const uint64_t d_lo16 = g.d_lo & ~15ull;
-        e = cudaMemcpyAsync(win_src, src + g.s_lo, g.s_hi - g.s_lo, cudaMemcpyHostToDevice, s);
+        // uploaded source bytes [up_lo, up_hi) >= [s_lo, s_hi); address of source byte s_lo / destination byte d_lo16
+        uint64_t up_lo = g.s_lo, up_hi = g.s_hi;
+        uint8_t* win_src = (uint8_t*)c.slot_src[k] + (g.s_lo & 15u);
+        uint8_t* win_dst = (uint8_t*)c.slot_dst[k];
+        if (align_copies) {
+            up_lo -= std::min<uint64_t>(g.s_lo, (uintptr_t)(src + g.s_lo) & (kCopyAlign - 1));
+            up_hi = std::min<uint64_t>(src_bytes, g.s_hi + ((kCopyAlign - ((uintptr_t)(src + g.s_hi) & (kCopyAlign - 1))) & (kCopyAlign - 1)));
+            win_src = (uint8_t*)c.slot_src[k] + ((uintptr_t)(src + up_lo) & (kCopyAlign - 1)) + (g.s_lo - up_lo);
+            win_dst = (uint8_t*)c.slot_dst[k] + ((uintptr_t)(dst + d_lo16) & (kCopyAlign - 1));
+        }
+        e = cudaMemcpyAsync(win_src - (g.s_lo - up_lo), src + up_lo, up_hi - up_lo, cudaMemcpyHostToDevice, s);
         if (e == cudaSuccess && holes)
             e = cudaMemcpyAsync(win_dst, dst + d_lo16, g.d_hi - d_lo16, cudaMemcpyHostToDevice, s);
         if (e != cudaSuccess)
@@ -727,8 +724,8 @@ int batch_host(DeviceCtx& c, const mod_desc* user_descs, uint64_t user_n, const 
         args.tiles = d_tiles + g.t0;
         args.n_tiles = g.t1 - g.t0;
         args.tiles_per_entry = 0;
-        args.src_lo16 = ((uint64_t)(uintptr_t)win_src + 15u) & ~15ull;
-        args.src_hi16 = ((uint64_t)(uintptr_t)win_src + (g.s_hi - g.s_lo)) & ~15ull;
+        args.src_lo16 = ((uint64_t)(uintptr_t)(win_src - (g.s_lo - up_lo)) + 15u) & ~15ull;
+        args.src_hi16 = ((uint64_t)(uintptr_t)(win_src + (up_hi - g.s_lo))) & ~15ull;
         args.uniform_delta = uniform_delta;
         e = modk::launch_batch(args, s);
         g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -738,8 +735,16 @@ int batch_host(DeviceCtx& c, const mod_desc* user_descs, uint64_t user_n, const 
             e = cudaMemcpyAsync(dst + d_lo16, win_dst, g.d_hi - d_lo16, cudaMemcpyDeviceToHost, s);
         } else {
             for (const auto& r : runs) {
-                e = cudaMemcpyAsync(dst + r.first, win_dst + (r.first - d_lo16), r.second - r.first,
-                                    cudaMemcpyDeviceToHost, s);
+                // cut points: the run's ends and, for a long run, the 128-byte boundaries just inside them
+                uint64_t cut[4] = {r.first, r.first, r.second, r.second};
+                if (align_copies && split_downloads && r.second - r.first >= (64u << 10)) {
+                    cut[1] = r.first + ((kCopyAlign - ((uintptr_t)(dst + r.first) & (kCopyAlign - 1))) & (kCopyAlign - 1));
+                    cut[2] = r.second - ((uintptr_t)(dst + r.second) & (kCopyAlign - 1));
+                }
+                for (int q = 0; q < 3 && e == cudaSuccess; ++q)
+                    if (cut[q + 1] > cut[q])
+                        e = cudaMemcpyAsync(dst + cut[q], win_dst + (cut[q] - d_lo16), cut[q + 1] - cut[q],
+                                            cudaMemcpyDeviceToHost, s);
                 if (e != cudaSuccess)
                     break;
             }
@@ -1340,6 +1345,26 @@ int mod_shard_range(uint64_t total, int rank, int world, uint64_t* begin, uint64
     *begin = b;
     *end = e;
     return MOD_OK;
+}
+
+int64_t mod_group_descs(const mod_desc* descs, uint64_t n, uint64_t group_bytes, uint64_t dst_phase, uint64_t modulus,
+                        mod_desc* out, uint8_t* closes, uint64_t out_cap)
+{
+    MOD_ABI_BEGIN
+    if (n && !descs)
+        return fail(MOD_ERR_ARG, "mod_group_descs: descs is null");
+    if (modulus < 16 || (modulus & (modulus - 1)) != 0 || group_bytes < modulus)
+        return fail(MOD_ERR_ARG, "mod_group_descs: modulus must be a power of two >= 16 and <= group_bytes");
+    modcut::Cut cut;
+    modcut::cut_into_groups(descs, n, group_bytes, dst_phase, modulus, cut);
+    if (out || closes) {
+        if (cut.pieces.size() > out_cap || !out || !closes)
+            return fail(MOD_ERR_ARG, "mod_group_descs: %zu pieces do not fit the output capacity", cut.pieces.size());
+        std::copy(cut.pieces.begin(), cut.pieces.end(), out);
+        std::copy(cut.closes.begin(), cut.closes.end(), closes);
+    }
+    return (int64_t)cut.pieces.size();
+    MOD_ABI_END("mod_group_descs")
 }
 
 int64_t mod_shard_descs(const mod_desc* descs, uint64_t n, int rank, int world, mod_desc* out, uint64_t out_cap)

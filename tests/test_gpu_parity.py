@@ -420,6 +420,37 @@ def test_batch_host_buffers_pipelined(mb, layout, monkeypatch):
     assert (dst == want).all()
 
 
+@pytest.mark.parametrize("src_shift,dst_shift", [(0, 0), (16, 48), (5, 5), (3, 16), (128, 64)])
+@pytest.mark.parametrize("in_place", [False, True])
+def test_batch_host_copy_alignment(mb, src_shift, dst_shift, in_place, monkeypatch):
+    """The host-pointer batch path widens uploads and splits downloads at 128-byte boundaries of the HOST
+    addresses when the caller's buffers are 16-byte aligned, and keeps plain copies otherwise.  Byte-packed
+    entries (groups start anywhere), caller buffers at several phases, guard bytes either side of dst."""
+    monkeypatch.setenv("MOD_GROUP_BYTES", str(1 << 20))
+    n = 300
+    sizes = synth.entry_sizes_loguniform(n, 9 << 20, lo=1, hi=1 << 18, seed=31)
+    src_off = synth.packed_offsets(sizes) + 77
+    dst_off = src_off if in_place else synth.packed_offsets(sizes) + 1000
+    descs = mb.make_descs(src_off, dst_off, sizes, synth.entry_keys(n, seed=33))
+    total = int((src_off + sizes).max()) + 300
+    base = np.zeros(total + 4096 + 256, np.uint8)
+    a0 = (-base.ctypes.data) % 4096  # a page-aligned origin inside the array, then the requested phases
+    src = base[a0 + src_shift:a0 + src_shift + total]
+    src[:] = synth.payload(11, total)
+    if in_place:
+        dst = src
+        want = oracle.cycle_batch(descs, src.copy(), src.copy())
+    else:
+        dbase = np.full(total + 4096 + 256 + 1200, 0x5E, np.uint8)
+        d0 = (-dbase.ctypes.data) % 4096
+        dst = dbase[d0 + dst_shift:d0 + dst_shift + total + 1200]
+        want = oracle.cycle_batch(descs, src, dst.copy())
+    mb.cycle_batch(descs, src, dst)
+    assert (dst == want).all(), (src_shift, dst_shift, in_place)
+    if not in_place:
+        assert (dbase[:d0 + dst_shift] == 0x5E).all() and (dbase[d0 + dst_shift + total + 1200:] == 0x5E).all()
+
+
 def test_config3_16gib_multipart_sharded(mb):
     """BASELINE config 3 at FULL size: a 16 GiB set = 32 parts x 512 MiB (kuMaxArkSize, CArk.cpp:19),
     one (offset, len, key) per part, cut into 8 offset-range shards whose boundaries fall INSIDE

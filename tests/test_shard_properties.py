@@ -44,3 +44,54 @@ def test_shard_range_partitions(total, world):
         assert b == prev and b <= e
         prev = e
     assert prev == total
+
+
+@settings(max_examples=120, deadline=None)
+@given(st.lists(st.tuples(st.integers(0, 9000), st.integers(-2**31, 2**31 - 1), st.integers(0, 40)), min_size=1, max_size=60),
+       st.sampled_from([1024, 2048, 4096, 16384]), st.integers(0, 127), st.sampled_from([16, 128]))
+def test_group_cut_partitions_the_batch(entries, group_bytes, dst_phase, modulus):
+    """mod_group_descs (how the host-pointer batch path forms its pipeline groups): the pieces, ciphered one by one,
+    give the batch's bytes; pieces stay in order and tile their entries; a group boundary that falls inside an entry
+    sits on an aligned destination address; no group holds more than group_bytes + modulus bytes of payload."""
+    sizes = np.array([e[0] for e in entries], dtype=np.int64)
+    keys = np.array([e[1] for e in entries], dtype=np.int64)
+    gaps = np.array([e[2] for e in entries], dtype=np.int64)
+    src_off = np.zeros(len(sizes), np.int64)
+    src_off[1:] = np.cumsum(sizes[:-1])
+    dst_off = np.cumsum(gaps) + src_off  # monotone destination with holes
+    descs = mb.make_descs(src_off, dst_off, sizes, keys)
+    total = int(sizes.sum())
+    src = (np.arange(total, dtype=np.uint32) * 7 + 3).astype(np.uint8)
+    dst_len = int((dst_off + sizes).max()) + 1
+    want = oracle.cycle_batch(descs, src, np.zeros(dst_len, np.uint8))
+    pieces, closes = mb.group_descs(descs, group_bytes, dst_phase, modulus)
+    assert len(pieces) == len(closes) and closes[-1] == 1
+    got = np.zeros(dst_len, np.uint8)
+    oracle.cycle_batch(pieces, src, got)
+    assert (got == want).all()
+    assert int(pieces["len"].sum()) == total
+    # order preserved, pieces tile the source stream, every piece keeps its entry's src -> dst displacement
+    run = 0
+    ends_src = src_off + sizes
+    for p in pieces:
+        n = int(p["len"])
+        if n == 0:
+            continue
+        assert int(p["src_off"]) == run
+        i = int(np.searchsorted(ends_src, run, side="right"))  # the entry that holds source byte `run`
+        assert run + n <= int(ends_src[i]) and int(p["dst_off"]) - run == int(dst_off[i]) - int(src_off[i])
+        run += n
+    assert run == total
+    # boundaries and group sizes
+    acc = 0
+    ends = {int(o + n) for o, n in zip(dst_off, sizes)}
+    for p, c in zip(pieces, closes):
+        acc += int(p["len"])
+        if c:
+            end = int(p["dst_off"]) + int(p["len"])
+            if end not in ends:  # the boundary is inside an entry: it must be aligned
+                assert (dst_phase + end) % modulus == 0
+            assert acc <= group_bytes + modulus
+            acc = 0
+        else:
+            assert acc < group_bytes
