@@ -784,6 +784,7 @@ def run_gpu_arm(args) -> None:
                     # burst figure from a SHORT timed region (a cfg4 step moves 67 GB: 20 of them run into the board's
                     # power cap half way and the "burst" number becomes a mixture), then the sustained run
                     sub_args.steps = max(5, min(args.steps, 20 if w == "cfg2" else 5))
+                    sub_args.warmup = 3  # every 10 ms launch before the timed ones eats into the board's power budget
                     r = measure_workload(c, sub_args, w, full=False, sustain_s=1.5, cooldown_s=1.5)
                     extra[w] = {k: r[k] for k in ("value", "ms_per_step", "kernel_ms", "parity_bytes_checked",
                                                   "roofline", "config", "gpu_launches", "clocks")}
