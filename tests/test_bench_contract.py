@@ -32,6 +32,14 @@ def test_reference_arm_line():
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
 
 
+def test_reference_arm_other_ranks_exit_quietly():
+    """Under torchrun (N > 1) rank 0 alone runs and prints the reference arm; the other ranks exit 0 without work."""
+    env = dict(os.environ, RANK="3", LOCAL_RANK="3", WORLD_SIZE="8")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "8", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == "", out.stdout + out.stderr
+
+
 def test_device_payload_is_the_synth_stream():
     """bench.py generates its plaintext where the buffer lives (torch int64 splitmix64); it must be the
     same counter-based stream the oracle side regenerates window by window (tests/synth.py)."""
