@@ -95,3 +95,38 @@ def test_group_cut_partitions_the_batch(entries, group_bytes, dst_phase, modulus
             acc = 0
         else:
             assert acc < group_bytes
+
+
+def test_group_cut_known_cases():
+    """Hand-checked cuts: an entry that crosses the fill point is split at the aligned address just below it (just
+    above it when that would leave nothing), an entry that ends exactly on the fill point closes the group whole,
+    empty entries ride along, and the tail piece carries the jumped key."""
+    key = 0x13579BDF
+    # one 5000-byte entry at dst 100, groups of 2048, 128-byte alignment of (dst_phase = 28) + offset
+    descs = mb.make_descs([0], [100], [5000], [key])
+    pieces, closes = mb.group_descs(descs, 2048, 28, 128)
+    # fill point 100 + 2048 = 2148 -> (28 + 2148) % 128 = 0: already aligned; next 2148 + 2048 = 4196, also aligned
+    assert [(int(p["dst_off"]), int(p["len"])) for p in pieces] == [(100, 2048), (2148, 2048), (4196, 904)]
+    assert list(closes) == [1, 1, 1]
+    assert [int(p["key"]) for p in pieces] == [key, mb.key_jump(key, 2048), mb.key_jump(key, 4096)]
+    # same entry, phase 0: cuts move down to multiples of 128 of the destination offset
+    pieces, closes = mb.group_descs(descs, 2048, 0, 128)
+    assert [(int(p["dst_off"]), int(p["len"])) for p in pieces] == [(100, 1948), (2048, 2048), (4096, 1004)]
+    assert all((int(p["dst_off"]) + int(p["len"])) % 128 == 0 for p in pieces[:-1])
+    # small entries: 3 x 700 bytes packed from 0 with an empty one in between; the third entry crosses 2048
+    descs = mb.make_descs([0, 700, 700, 1400, 2100], [0, 700, 700, 1400, 2100], [700, 0, 700, 700, 50], [1, 2, 3, 4, 5])
+    pieces, closes = mb.group_descs(descs, 2048, 0, 128)
+    assert [(int(p["dst_off"]), int(p["len"])) for p in pieces] == [(0, 700), (700, 0), (700, 700), (1400, 648), (2048, 52), (2100, 50)]
+    assert list(closes) == [0, 0, 0, 1, 0, 1]
+    assert int(pieces[4]["key"]) == mb.key_jump(4, 648) and int(pieces[3]["key"]) == 4
+    # an entry that ends exactly on the fill point is not split
+    descs = mb.make_descs([0, 2048], [0, 2048], [2048, 10], [7, 8])
+    pieces, closes = mb.group_descs(descs, 2048, 0, 128)
+    assert [(int(p["dst_off"]), int(p["len"])) for p in pieces] == [(0, 2048), (2048, 10)] and list(closes) == [1, 1]
+    # a cut that would be empty moves UP instead: entry of 300 bytes at dst 2000, fill point 2048 -> aligned 2048 - 2000 = 48
+    descs = mb.make_descs([0, 2000], [0, 2000], [2000, 300], [7, 8])
+    pieces, closes = mb.group_descs(descs, 2048, 0, 128)
+    assert [(int(p["dst_off"]), int(p["len"])) for p in pieces] == [(0, 2000), (2000, 48), (2048, 252)]
+    descs = mb.make_descs([0], [2047], [300], [9])  # fill point 2047 + 2048 = 4095: beyond the entry -> whole, closes at the end
+    pieces, closes = mb.group_descs(descs, 2048, 0, 128)
+    assert [(int(p["dst_off"]), int(p["len"])) for p in pieces] == [(2047, 300)] and list(closes) == [1]
